@@ -1,0 +1,37 @@
+# Builds the sm_100a device backend (C ABI in include/spn_b200.h), the C++ host
+# layer and the BS executables.  nvcc cross-compiles without a GPU.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude $(SPN_TUNE)
+CSRC      := streamparanumal_b200/csrc
+LIBDIR    := streamparanumal_b200/lib
+
+KERNEL_SRCS := $(CSRC)/runtime.cu $(CSRC)/stream_abi.cu $(CSRC)/ogs_abi.cu
+KERNEL_HDRS := $(CSRC)/common.cuh $(CSRC)/stream_kernels.cuh $(CSRC)/ogs_kernels.cuh include/spn_b200.h
+
+all: $(LIBDIR)/libspn_b200.so $(LIBDIR)/libspn_b200_comm.so
+
+$(LIBDIR)/libspn_b200.so: $(KERNEL_SRCS) $(KERNEL_HDRS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(KERNEL_SRCS) -cudart static
+
+$(LIBDIR)/libspn_b200_comm.so: $(CSRC)/comm_nccl.cu include/spn_b200.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/comm_nccl.cu -cudart static -lnccl
+
+ptxas-info:
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/stream_abi.cu 2>&1 | grep -E "Compiling|registers|spill"
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/ogs_abi.cu 2>&1 | grep -E "Compiling|registers|spill"
+
+clean:
+	rm -rf $(LIBDIR)/*.so build
+
+.PHONY: all clean ptxas-info
+
+# ---- tuning tools (run on the GPU box) ----------------------------------------------
+tune: build/tune_stream
+build/tune_stream: tools/tune_stream.cu $(KERNEL_HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -o $@ tools/tune_stream.cu
+.PHONY: tune

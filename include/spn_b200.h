@@ -1,0 +1,192 @@
+/*
+ * spn_b200.h — C ABI of the B200-native (sm_100a) device backend for
+ * streamParanumal's hot path (BS0–BS8).
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one OCCA
+ * kernel / device-runtime call that the reference makes on this path; the
+ * reference interface each one stands in for is cited as
+ * <reference file>:<line> (paths relative to the streamParanumal tree).
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; no C++/torch types.
+ *  - all device pointers are BORROWED (obtained from spn_malloc, or any other
+ *    CUDA allocation in the same process, e.g. deviceMemory<T>::ptr() in the
+ *    reference, include/memory.hpp:308-313).  The ABI never allocates results.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    Kernels are enqueued on it and the call returns immediately, exactly like
+ *    occa::kernel::operator() on the CUDA backend
+ *    (occa/src/occa/internal/modes/cuda/kernel.cpp:74-101).
+ *  - return value: 0 on success; >0 is a cudaError_t; <0 is an spn error code
+ *    (see spn_status).  spn_error_string() renders either.  The C++ host layer
+ *    converts non-zero into libp::exception semantics (include/utils.hpp:57-75).
+ *  - zero-sized work (n==0, NrowBlocks==0) is a successful no-op, and NULL
+ *    pointers are accepted in that case (reference: skipped launches at
+ *    libs/ogs/ogsOperator.cpp:186,195,304,313,451,461 and null handles at P=1).
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef SPN_B200_H
+#define SPN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* spn_stream_t; /* cudaStream_t */
+typedef void* spn_event_t;  /* cudaEvent_t  */
+
+typedef enum {
+  SPN_SUCCESS = 0,
+  SPN_ERR_INVALID_ARGUMENT = -1,
+  SPN_ERR_UNSUPPORTED = -2, /* e.g. not an sm_100 device */
+  SPN_ERR_ROW_TOO_LONG = -3, /* a row block exceeds spn_ogs_nodes_per_block() */
+  SPN_ERR_NCCL = -4,
+  SPN_ERR_NO_DEVICE = -5
+} spn_status;
+
+/* element type / reduction op: numeric values equal the reference enums
+ * ogs::Type {Float,Double,Int32,Int64} and ogs::Op {Add,Mul,Max,Min}
+ * (include/ogs.hpp:178-191). */
+typedef enum { SPN_FLOAT = 0, SPN_DOUBLE = 1, SPN_INT32 = 2, SPN_INT64 = 3 } spn_type;
+typedef enum { SPN_ADD = 0, SPN_MUL = 1, SPN_MAX = 2, SPN_MIN = 3 } spn_op;
+
+const char* spn_error_string(int status);
+int spn_version(void);
+
+/* ------------------------------------------------------------------------
+ * Device runtime — replaces the slice of occa::device / occa::memory /
+ * occa::stream that platform_t, deviceMemory<T> and ogs touch
+ * (include/platform.hpp:95-154, include/memory.hpp:284-454,
+ *  occa/src/occa/internal/modes/cuda/{device,buffer,memory,stream}.cpp).
+ * ---------------------------------------------------------------------- */
+int spn_device_count(int* count);                 /* occa::getDeviceCount("CUDA"), include/platform.hpp:165 */
+int spn_set_device(int device_id);                /* device.setup("{mode:'CUDA',device_id:..}"), libs/core/platformDeviceConfig.cpp:159 */
+int spn_get_device(int* device_id);
+int spn_device_sm_count(int* sms);
+int spn_device_sync(void);
+int spn_stream_create(spn_stream_t* stream);      /* device.createStream(), libs/ogs/ogsSetup.cpp:103-104 */
+int spn_stream_destroy(spn_stream_t stream);
+int spn_stream_sync(spn_stream_t stream);         /* device.finish() = cuStreamSynchronize(current), occa/src/core/device.cpp:250-254 */
+int spn_malloc(void** dptr, size_t bytes);        /* cuMemAlloc, uninitialised: occa/.../cuda/buffer.cpp:65-67 */
+int spn_free(void* dptr);
+int spn_host_malloc(void** hptr, size_t bytes);   /* pinned host: platform.hostMalloc, include/platform.hpp:117-140 */
+int spn_host_free(void* hptr);
+int spn_memset(void* dptr, int value, size_t bytes, spn_stream_t stream);
+/* copyFrom/copyTo; async!=0 == props["async"]=true (enqueue on stream, no host wait),
+ * occa/.../cuda/memory.cpp:59-139.  bytes==0 is a no-op (include/memory.hpp:338,372,400,434). */
+int spn_memcpy_h2d(void* dst, const void* src, size_t bytes, spn_stream_t stream, int async);
+int spn_memcpy_d2h(void* dst, const void* src, size_t bytes, spn_stream_t stream, int async);
+int spn_memcpy_d2d(void* dst, const void* src, size_t bytes, spn_stream_t stream, int async);
+/* events: device-side timing and stream ordering without host syncs (replaces the
+ * device.finish() pairs at libs/ogs/ogs.cpp:74,104,117). */
+int spn_event_create(spn_event_t* ev);
+int spn_event_destroy(spn_event_t ev);
+int spn_event_record(spn_event_t ev, spn_stream_t stream);
+int spn_event_sync(spn_event_t ev);
+int spn_stream_wait_event(spn_stream_t stream, spn_event_t ev);
+int spn_event_elapsed_ms(spn_event_t start, spn_event_t stop, float* ms);
+
+/* ------------------------------------------------------------------------
+ * BS0–BS5 streaming kernels (FP64 = dfloat, include/types.h:33-69).
+ * n is the reference's `dlong N` widened to 64 bits.
+ *
+ * Reductions need a device workspace of spn_reduce_workspace_bytes() bytes that
+ * must not be shared by launches that may run concurrently.  The caller
+ * zero-fills it once (spn_memset) before first use; launches leave it re-armed.
+ * Pass NULL to use a per-device internal workspace (single stream use only).
+ * ---------------------------------------------------------------------- */
+size_t spn_reduce_workspace_bytes(void);
+
+/* bs0(N,a,b): empty 1x1 launch.            BS/BS0/okl/bs0.okl:27-39, call site BS/BS0/src/bs0Run.cpp:53,72 */
+int spn_bs0(int N, const double* a, double* b, spn_stream_t stream);
+/* bs1(N,a,b): b[i]=a[i].                    BS/BS1/okl/bs1.okl:27-34, BS/BS1/src/bs1Run.cpp:54,76 */
+int spn_copy_f64(int64_t n, const double* a, double* b, spn_stream_t stream);
+/* bs2(N,alpha,x,beta,y): y=alpha*x+beta*y, unfused mul/mul/add as the Serial
+ * reference computes it (-O3, no FMA).      BS/BS2/okl/bs2.okl:27-36, BS/BS2/src/bs2Run.cpp:57,79 */
+int spn_axpby_f64(int64_t n, double alpha, const double* x, double beta, double* y, spn_stream_t stream);
+/* bs3_1+bs3_2 fused: out[0]=sum a[i]^2.     BS/BS3/okl/bs3.okl:27-102, BS/BS3/src/bs3Run.cpp:58-59,83-84 */
+int spn_norm2_f64(int64_t n, const double* a, double* out, void* workspace, spn_stream_t stream);
+/* bs4_1+bs4_2 fused: out[0]=sum a[i]*b[i].  BS/BS4/okl/bs4.okl:27-103, BS/BS4/src/bs4Run.cpp:58-59,83-84 */
+int spn_dot_f64(int64_t n, const double* a, const double* b, double* out, void* workspace, spn_stream_t stream);
+/* bs5_1+bs5_2 fused: r+=alpha*Ap (unfused mul+add); rdotr[0]=sum r_new^2.
+ *                                            BS/BS5/okl/bs5.okl:27-106, BS/BS5/src/bs5Run.cpp:62-63,87-88 */
+int spn_cg_update_f64(int64_t n, const double* Ap, double alpha, double* r, double* rdotr, void* workspace, spn_stream_t stream);
+
+/* Two-launch entry points with the reference kernels' exact argument lists, for a
+ * kernel_t-level binding (kernel1/kernel2 of bs3/bs4/bs5).  *_1 ignores the
+ * Nblocks launch hint for its own grid, leaves the finished sum in tmp[0] and
+ * +0.0 in tmp[1..Nblocks); *_2 sums tmp[0..Nblocks) into out[0] as the reference
+ * second pass does. */
+int spn_bs3_1(int Nblocks, int N, const double* a, double* tmp, spn_stream_t stream);
+int spn_bs3_2(int Nblocks, const double* tmp, double* out, spn_stream_t stream);
+int spn_bs4_1(int Nblocks, int N, const double* a, const double* b, double* tmp, spn_stream_t stream);
+int spn_bs4_2(int Nblocks, const double* tmp, double* out, spn_stream_t stream);
+int spn_bs5_1(int Nblocks, int N, const double* Ap, double alpha, double* r, double* tmp, spn_stream_t stream);
+int spn_bs5_2(int Nblocks, const double* tmp, double* out, spn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * ogs kernels (libs/ogs/okl/ogsKernels.okl).  Argument lists follow the
+ * reference kernel_t calls; `type`/`op` replace the JIT defines T, OGS_OP_INIT,
+ * OGS_OP (libs/ogs/ogsUtils.cpp:46-123).  All index arrays are int32 (dlong).
+ *
+ * Row blocks: blockRowStarts[0..NrowBlocks] partitions the rows so that no
+ * block holds more than spn_ogs_nodes_per_block() non-zeros — the value the
+ * host must use where the reference uses ogs::gatherNodesPerBlock=512
+ * (include/ogs/ogsOperator.hpp:37-38, libs/ogs/ogsOperator.cpp:522-594).
+ * Blocks built with a smaller limit (e.g. the reference's 512) are accepted.
+ * Sums fold in CSR order starting from the op identity, so results are
+ * bit-identical to the reference Serial kernels.
+ * ---------------------------------------------------------------------- */
+int spn_ogs_nodes_per_block(void);
+
+/* gather(NrowBlocks,k,blockRowStarts,rowStarts,colIds,v,gv)
+ *   gv[k+row*K] = OP_{g in row} v[k+colIds[g]*K]
+ * libs/ogs/okl/ogsKernels.okl:86-122; call site libs/ogs/ogsOperator.cpp:187-202 */
+int spn_ogs_gather(int NrowBlocks, int K, const int* blockRowStarts, const int* rowStarts,
+                   const int* colIds, const void* v, void* gv, int type, int op, spn_stream_t stream);
+/* scatter(NrowBlocks,k,blockRowStarts,rowStarts,colIds,gv,v)
+ *   v[k+colIds[g]*K] = gv[k+row*K]
+ * libs/ogs/okl/ogsKernels.okl:127-164; call site libs/ogs/ogsOperator.cpp:305-320 */
+int spn_ogs_scatter(int NrowBlocks, int K, const int* blockRowStarts, const int* rowStarts,
+                    const int* colIds, const void* gv, void* v, int type, spn_stream_t stream);
+/* gatherScatter(NrowBlocks,k,blockRowStarts,gRowStarts,gColIds,sRowStarts,sColIds,v), in place.
+ * blockRowStarts must bound BOTH CSRs' block sizes.
+ * libs/ogs/okl/ogsKernels.okl:32-81; call site libs/ogs/ogsOperator.cpp:452-479 */
+int spn_ogs_gather_scatter(int NrowBlocks, int K, const int* blockRowStarts,
+                           const int* gRowStarts, const int* gColIds,
+                           const int* sRowStarts, const int* sColIds,
+                           void* v, int type, int op, spn_stream_t stream);
+/* extract(N,k,ids,q,gatherq): gatherq[n]=q[n%K + ids[n/K]*K]
+ * libs/ogs/okl/ogsKernels.okl:167-177; call site libs/ogs/ogsPairwise.cpp:115 */
+int spn_ogs_extract(int N, int K, const int* ids, const void* q, void* gatherq, int type,
+                    spn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Device-buffer communication over NCCL — replaces comm_t::{Isend,Irecv,
+ * Waitall} on device pointers (libs/ogs/ogsPairwise.cpp:135-152) and adds the
+ * scalar allreduce the north-star asks for after norm/dot/rdotr.
+ * Lives in libspn_b200_comm.so so the kernel library carries no NCCL dependency.
+ * ---------------------------------------------------------------------- */
+typedef struct spn_comm* spn_comm_t;
+#define SPN_UNIQUE_ID_BYTES 128
+int spn_comm_unique_id(void* id128);                       /* rank 0: ncclGetUniqueId */
+int spn_comm_init(spn_comm_t* comm, const void* id128, int rank, int size);
+int spn_comm_destroy(spn_comm_t comm);
+int spn_comm_rank(spn_comm_t comm, int* rank);
+int spn_comm_size(spn_comm_t comm, int* size);
+/* one grouped pairwise exchange: for r<nrecv post recv of recvBytes[r] from
+ * recvRanks[r] into recvBuf+recvOffsets[r]; for s<nsend send sendBytes[s] to sendRanks[s]
+ * from sendBuf+sendOffsets[s] (offsets in bytes), all on `stream`. */
+int spn_comm_exchange(spn_comm_t comm,
+                      int nrecv, const int* recvRanks, const size_t* recvOffsets, const size_t* recvBytes, void* recvBuf,
+                      int nsend, const int* sendRanks, const size_t* sendOffsets, const size_t* sendBytes, const void* sendBuf,
+                      spn_stream_t stream);
+int spn_comm_allreduce_sum_f64(spn_comm_t comm, double* buf, int count, spn_stream_t stream);
+int spn_comm_barrier(spn_comm_t comm, spn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPN_B200_H */
