@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py — the driver-facing benchmark of the BS hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BS8, the reference's fused ogs gather+scatter benchmark
+(BS/BS8/src/bs8Run.cpp:29-78) on the configuration BASELINE.json quotes it on — a box
+of 64x64x64 degree-7 hex elements PER RANK (2^27 local nodes, FP64, K=1, Add, Sym).
+One "step" is one mesh.ogs.GatherScatter(o_q, 1, Add, Sym) call.  `value` is the
+reference's DOFs/s figure (NgatherGlobal / time per call: bs8Run.cpp:67-75) summed over
+all ranks, in GDOF/s, with q resident in HBM; `e2e` is the same metric through the
+host-memory overload (pinned host q -> H2D -> gatherScatter -> D2H every step).
+With --suite (default on at 1 GPU) the same JSON line carries a `suite` object with the
+effective GB/s of every BS1-BS8 kernel at its BASELINE.json size and BS0 us/launch,
+bytes counted the way the reference counts them.
+
+--impl reference times the reference's own CPU kernels (oracle/_ref: the OKL sources
+compiled for the host; plus the OpenMP-threaded restatement of the reference's host
+twins) on a bounded sample of the same workload on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
+def bs8_bytes(Nt, Ng):
+    """BS/BS8/src/bs8Run.cpp:58-61"""
+    return 4 * (Ng + 1) + 4 * Nt + 8 * Nt + 8 * Nt
+
+
+def bs6_bytes(Nt, Ng):
+    """BS/BS6/src/bs6Run.cpp:60-63 (BS7 counts the same total: bs7Run.cpp:60-63)"""
+    return 4 * (Ng + 1) + 4 * Nt + 8 * Nt + 8 * Ng
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+
+    def __init__(self, device_index):
+        self.rows = []
+        self.proc = None
+        self.idx = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={SMI_QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smmax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smmax) if smmax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm (CPU)
+# --------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import spn_testutil as util
+    from oracle import pyoracle
+
+    cores = os.cpu_count() or 1
+    nx = args.ref_nx
+    ids = util.hex_ids(nx, nx, nx, args.p)
+    rs, ci = util.csr_from_ids(ids)
+    Nt, Ng = ids.size, rs.size - 1
+    q = util.splitmix64(Nt, 3)
+    have_ref = pyoracle.have_ref()
+    blocks = pyoracle.block_rows(rs, 512) if have_ref else None
+
+    def ref_serial():
+        # the reference's gatherScatter OKL kernel, Serial semantics.  OCCA's OpenMP mode puts its
+        # parallel-for on the k<K loop (one iteration here), so this is also the OpenMP-mode speed.
+        pyoracle.ref_ogs_gather_scatter(blocks, rs, ci, rs, ci, q)
+
+    def port_threaded():
+        # restatement of the reference's threaded host twin (libs/ogs/ogsOperator.cpp:340-409)
+        pyoracle.ogs_gather_scatter(rs, ci, rs, ci, q, threads=cores)
+
+    def time_fn(fn):
+        for _ in range(args.warmup):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        return (time.perf_counter() - t0) / args.steps
+
+    results = {}
+    if have_ref:
+        results["reference"] = time_fn(ref_serial)
+    results["port"] = time_fn(port_threaded)
+    kind = min(results, key=results.get)
+    t = results[kind]
+    value = Ng / t * 1e-9
+    sample = (f"BS8 gatherScatter on a {nx}^3 degree-{args.p} hex box (Nt={Nt}, Ng={Ng}), "
+              f"{args.steps} calls after {args.warmup} warm-ups; host arrays (pyoracle copies v per call)")
+    line = {
+        "impl": "reference", "metric": "BS8 gather+scatter throughput (DOFs/s, NgatherGlobal per call time)",
+        "value": value, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BS8 ogs gatherScatter, hex p={args.p}, {nx}^3 elements (bounded CPU sample of the 64^3 workload)",
+                   "nx": nx, "p": args.p, "Nt": Nt, "Ng": Ng},
+        "effective_gbs": bs8_bytes(Nt, Ng) / t * 1e-9,
+        "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": cores if kind == "port" else 1, "kind": kind,
+                         "sample": sample,
+                         "all": {k: {"GDOF/s": Ng / v * 1e-9, "GB/s": bs8_bytes(Nt, Ng) / v * 1e-9,
+                                     "cores": cores if k == "port" else 1} for k, v in results.items()}},
+        "e2e": {"value": value, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+def cuda_time(fn, iters, warm, torch):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / iters
+
+
+def run_suite(torch, K, peak, ogs_ctx):
+    """BS0-BS7 at the BASELINE.json sizes (BS8 is the headline and is added by the caller)."""
+    out = {}
+    dev = "cuda"
+
+    def add(name, bytes_per_call, t, dofs):
+        out[name] = {"ms": t * 1e3, "GB/s": bytes_per_call / t * 1e-9, "frac_of_measured_peak": bytes_per_call / t * 1e-9 / peak,
+                     "frac_of_8TBs": bytes_per_call / t * 1e-9 / 8000.0, "GDOF/s": dofs / t * 1e-9, "bytes": bytes_per_call}
+
+    # BS1-BS4 at the top of the sweep (4 GiB moved), BS5 at N=2^26 (config 1)
+    B = 1 << 32
+    n1 = B // 16
+    a = torch.rand(n1, dtype=torch.float64, device=dev)
+    b = torch.empty_like(a)
+    add("BS1 copy", 16 * n1, cuda_time(lambda: K.copy(n1, a, b), 20, 5, torch), n1)
+    n2 = B // 24
+    add("BS2 axpby", 24 * n2, cuda_time(lambda: K.axpby(n2, 1.0, a, 1.0, b), 20, 5, torch), n2)
+    n4 = B // 16
+    o = torch.zeros(1, dtype=torch.float64, device=dev)
+    add("BS4 dot", 16 * n4, cuda_time(lambda: K.dot(n4, a, b, o), 20, 5, torch), n4)
+    del b
+    n3 = B // 8
+    a3 = torch.cat([a, a])
+    del a
+    add("BS3 norm", 8 * n3, cuda_time(lambda: K.norm2(n3, a3, o), 20, 5, torch), n3)
+    del a3
+    n5 = 1 << 26
+    Ap = torch.rand(n5, dtype=torch.float64, device=dev)
+    r = torch.zeros(n5, dtype=torch.float64, device=dev)
+    add("BS5 cg_update", 24 * n5, cuda_time(lambda: K.cg_update(n5, Ap, 1.0, r, o), 20, 5, torch), n5)
+    # BS0: launch latency per launch, host wall clock around 1000 launches (bs0Run.cpp:70-77)
+    for _ in range(100):
+        K.bs0(1, Ap, r)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(1000):
+        K.bs0(1, Ap, r)
+    torch.cuda.synchronize()
+    out["BS0 launch"] = {"us_per_launch": (time.perf_counter() - t0) / 1000 * 1e6}
+    del Ap, r
+    # BS6 / BS7 on the headline mesh
+    nb, d_bs, d_rs, d_ci, Nt, Ng, q = ogs_ctx
+    gq = torch.empty(Ng, dtype=torch.float64, device=dev)
+    add("BS6 gather", bs6_bytes(Nt, Ng), cuda_time(lambda: K.ogs_gather(nb, 1, d_bs, d_rs, d_ci, q, gq), 20, 5, torch), Ng)
+    add("BS7 scatter", bs6_bytes(Nt, Ng), cuda_time(lambda: K.ogs_scatter(nb, 1, d_bs, d_rs, d_ci, gq, q), 20, 5, torch), Ng)
+    return out
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import spn_testutil as util
+    from streamparanumal_b200 import kernels as K
+    from streamparanumal_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: streamparanumal_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    _lib.kernel_lib()  # fail loudly if the sm_100a library is missing
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peak, peak_src = measured_peak()
+
+    # ---- setup: mesh -> CSR (host, once; not timed — the reference does not time it either) ----
+    nx, p = args.nx, args.p
+    t_setup = time.perf_counter()
+    ids = util.hex_ids(nx, nx, nx, p)
+    rs, ci = util.csr_from_ids(ids)
+    del ids
+    bs = util.greedy_blocks(rs, K.nodes_per_block())
+    Nt, Ng, nb = ci.size, rs.size - 1, bs.size - 1
+    t_setup = time.perf_counter() - t_setup
+    d_bs, d_rs, d_ci = (torch.from_numpy(x).cuda() for x in (bs, rs, ci))
+    q = torch.from_numpy(util.splitmix64(Nt, 3 + rank)).cuda()
+
+    if world > 1:
+        raise SystemExit("multi-GPU BS8 (halo exchange) is not wired into bench.py yet")
+
+    step = lambda: K.ogs_gather_scatter(nb, 1, d_bs, d_rs, d_ci, d_rs, d_ci, q)
+
+    # ---- timed region: device-resident ----
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t_step = e0.elapsed_time(e1) * 1e-3 / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers through the C ABI (pinned host q -> H2D -> kernel -> D2H), every step ----
+    lib = _lib.kernel_lib()
+    import ctypes
+    nbytes = Nt * 8
+    hq = ctypes.c_void_p()
+    _lib.check(lib.spn_host_malloc(ctypes.byref(hq), nbytes), "host_malloc")
+    hq_np = np.ctypeslib.as_array(ctypes.cast(hq, ctypes.POINTER(ctypes.c_double)), shape=(Nt,))
+    hq_np[:] = util.splitmix64(Nt, 11)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def e2e_step():
+        _lib.check(lib.spn_memcpy_h2d(q.data_ptr(), hq, nbytes, st, 1), "h2d")
+        step()
+        _lib.check(lib.spn_memcpy_d2h(hq, q.data_ptr(), nbytes, st, 1), "d2h")
+
+    e2e_steps = max(3, min(args.steps, 10))
+    t_e2e = cuda_time(e2e_step, e2e_steps, 2, torch)
+    _lib.check(lib.spn_host_free(hq), "host_free")
+
+    line = {
+        "metric": "BS8 gather+scatter throughput (DOFs/s, NgatherGlobal per call time)",
+        "value": Ng * world / t_step * 1e-9, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BS8 ogs gatherScatter(Add,Sym,K=1), hex p={p}, {nx}^3 elements per rank",
+                   "nx": nx, "p": p, "Nt_per_rank": Nt, "Ng_per_rank": Ng, "row_blocks": nb,
+                   "l2": "q (1.07 GB) + CSR (0.9 GB) per call exceed the 126 MB L2; no flush needed",
+                   "host_setup_s": round(t_setup, 2)},
+        "effective_gbs": bs8_bytes(Nt, Ng) * world / t_step * 1e-9,
+        "roofline": {"bound": "hbm", "kernel": "gather_scatter_sym_kernel<double,Add>",
+                     "achieved": bs8_bytes(Nt, Ng) / t_step * 1e-9, "peak": peak, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": bs8_bytes(Nt, Ng) / t_step * 1e-9 / peak,
+                     "frac_of_8TBs_nominal": bs8_bytes(Nt, Ng) / t_step * 1e-9 / 8000.0,
+                     "algorithmic_bytes_per_launch": bs8_bytes(Nt, Ng), "traffic": None},
+        "e2e": {"value": Ng * world / t_e2e * 1e-9, "unit": "GDOF/s", "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+    }
+
+    if args.suite and world == 1:
+        line["suite"] = run_suite(torch, K, peak, (nb, d_bs, d_rs, d_ci, Nt, Ng, q))
+        line["suite"]["BS8 gatherScatter"] = {"ms": t_step * 1e3, "GB/s": line["effective_gbs"],
+                                              "frac_of_measured_peak": line["roofline"]["frac"],
+                                              "frac_of_8TBs": line["roofline"]["frac_of_8TBs_nominal"],
+                                              "GDOF/s": line["value"], "bytes": bs8_bytes(Nt, Ng)}
+
+    if args.cpu_baseline and rank == 0:
+        line["cpu_baseline"] = cpu_baseline(args)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline(args):
+    """The reference's CPU kernels on this box's host cores, bounded sample (rank 0, N=1)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import spn_testutil as util
+    from oracle import pyoracle
+    cores = os.cpu_count() or 1
+    nx = args.ref_nx
+    ids = util.hex_ids(nx, nx, nx, args.p)
+    rs, ci = util.csr_from_ids(ids)
+    Nt, Ng = ids.size, rs.size - 1
+    q = util.splitmix64(Nt, 3)
+    res = {}
+    if pyoracle.have_ref():
+        blocks = pyoracle.block_rows(rs, 512)
+        pyoracle.ref_ogs_gather_scatter(blocks, rs, ci, rs, ci, q)
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < 6.0:
+            pyoracle.ref_ogs_gather_scatter(blocks, rs, ci, rs, ci, q)
+            n += 1
+        res["reference"] = (time.perf_counter() - t0) / n
+    pyoracle.ogs_gather_scatter(rs, ci, rs, ci, q, threads=cores)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < 6.0:
+        pyoracle.ogs_gather_scatter(rs, ci, rs, ci, q, threads=cores)
+        n += 1
+    res["port"] = (time.perf_counter() - t0) / n
+    kind = min(res, key=res.get)
+    return {"value": Ng / res[kind] * 1e-9, "unit": "GDOF/s", "cores": cores if kind == "port" else 1, "kind": kind,
+            "sample": f"BS8 gatherScatter, {nx}^3 degree-{args.p} hex box (Nt={Nt}), ~6 s per variant",
+            "all": {k: {"GDOF/s": Ng / v * 1e-9, "GB/s": bs8_bytes(Nt, Ng) / v * 1e-9, "cores": cores if k == "port" else 1}
+                    for k, v in res.items()}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=64, help="elements per direction per rank (reference -nx/-ny/-nz)")
+    ap.add_argument("--p", type=int, default=7, help="polynomial degree (reference -p)")
+    ap.add_argument("--ref-nx", type=int, default=24, help="CPU sample size for the reference arm / cpu_baseline")
+    ap.add_argument("--no-suite", dest="suite", action="store_false")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -164,6 +164,34 @@ int spn_ogs_extract(int N, int K, const int* ids, const void* q, void* gatherq, 
                     spn_stream_t stream);
 
 /* ------------------------------------------------------------------------
+ * ogs operator plan — the B200-native device form of ogsOperator_t
+ * (include/ogs/ogsOperator.hpp:44-138; ctor libs/ogs/ogsOperator.cpp:597-665, which
+ * uploads rowStarts/colIds and the blockRowStarts launch partition of :522-594).
+ * spn_ogs_plan_create replaces that upload step: from the HOST rowStarts it cuts the
+ * rows into warp tiles (<=32 non-zeros, whole rows) and stores one 16-byte descriptor
+ * per tile on the device; the kernels then read colIds + descriptors instead of
+ * colIds + rowStarts + blockRowStarts.  d_rowStarts / d_colIds are BORROWED device
+ * arrays that must outlive the plan.  The three calls are the device Gather /
+ * Scatter / GatherScatter of libs/ogs/ogsOperator.cpp:176-204, 295-322, 442-481 for
+ * one CSR (gather CSR == scatter CSR, i.e. every case of an Unsigned operator and
+ * Sym on a Signed one); sums fold in CSR order from the op identity (bit-identical
+ * to the reference Serial kernels).  Built once at setup, like the reference operator.
+ * ---------------------------------------------------------------------- */
+typedef struct spn_ogs_plan* spn_ogs_plan_t;
+int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, const int* h_rowStarts,
+                        const int* d_rowStarts, const int* d_colIds);
+int spn_ogs_plan_destroy(spn_ogs_plan_t plan);
+int spn_ogs_plan_info(spn_ogs_plan_t plan, int* Ntiles, int* Nirregular, size_t* plan_bytes);
+int spn_ogs_plan_gather(spn_ogs_plan_t plan, int K, const void* v, void* gv, int type, int op, spn_stream_t stream);
+int spn_ogs_plan_scatter(spn_ogs_plan_t plan, int K, const void* gv, void* v, int type, spn_stream_t stream);
+int spn_ogs_plan_gather_scatter(spn_ogs_plan_t plan, int K, void* v, int type, int op, spn_stream_t stream);
+/* out-of-place form: w[col] = OP_{col' in row(col)} v[col'] for every column of the operator
+ * (entries of w outside the operator are left untouched) */
+int spn_ogs_plan_gather_scatter_to(spn_ogs_plan_t plan, int K, const void* v, void* w, int type, int op, spn_stream_t stream);
+/* tuning/experiment knob (key 0: kernel variant); not part of the drop-in surface */
+int spn_debug_set(int key, int value);
+
+/* ------------------------------------------------------------------------
  * Device-buffer communication over NCCL — replaces comm_t::{Isend,Irecv,
  * Waitall} on device pointers (libs/ogs/ogsPairwise.cpp:135-152) and adds the
  * scalar allreduce the north-star asks for after norm/dot/rdotr.

@@ -9,7 +9,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
-KERNEL_LIB = os.path.join(LIB_DIR, "libspn_b200.so")
+# SPN_B200_LIB points tuning runs at an alternative build of the same library
+KERNEL_LIB = os.environ.get("SPN_B200_LIB") or os.path.join(LIB_DIR, "libspn_b200.so")
 COMM_LIB = os.path.join(LIB_DIR, "libspn_b200_comm.so")
 HOST_LIB = os.path.join(LIB_DIR, "libspn_host.so")
 
@@ -67,6 +68,14 @@ KERNEL_SIGNATURES = {
     "spn_ogs_scatter": [c_int, c_int, _IP, _IP, _IP, _P, _P, c_int, _P],
     "spn_ogs_gather_scatter": [c_int, c_int, _IP, _IP, _IP, _IP, _IP, _P, c_int, c_int, _P],
     "spn_ogs_extract": [c_int, c_int, _IP, _P, _P, c_int, _P],
+    "spn_ogs_plan_create": [POINTER(c_void_p), c_int, _IP, _IP, _IP],
+    "spn_ogs_plan_destroy": [_P],
+    "spn_ogs_plan_info": [_P, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)],
+    "spn_ogs_plan_gather": [_P, c_int, _P, _P, c_int, c_int, _P],
+    "spn_ogs_plan_scatter": [_P, c_int, _P, _P, c_int, _P],
+    "spn_ogs_plan_gather_scatter": [_P, c_int, _P, c_int, c_int, _P],
+    "spn_ogs_plan_gather_scatter_to": [_P, c_int, _P, _P, c_int, c_int, _P],
+    "spn_debug_set": [c_int, c_int],
 }
 
 COMM_SIGNATURES = {

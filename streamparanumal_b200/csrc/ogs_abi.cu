@@ -1,16 +1,45 @@
 // C-ABI entry points for the ogs kernels (include/spn_b200.h).  `type`/`op`
 // select a precompiled instantiation where the reference JIT-compiles one OKL
 // kernel per (T, OGS_OP) pair (libs/ogs/ogsUtils.cpp:46-123).
-#include "ogs_kernels.cuh"
+#include "ogs_pipe.cuh"
+
+#ifndef SPN_OGS_THREADS
+#define SPN_OGS_THREADS 512
+#endif
 
 using namespace spn;
 
 namespace {
 
+// Persistent launch of the pipelined kernels: grid.x = min(NrowBlocks, SMs x resident CTAs),
+// grid.y = K.  The occupancy query and the opt-in to >48 KB dynamic shared memory run once
+// per instantiation and device.
+template <typename T, int OP, int MODE>
+void launch_pipe(dim3 grid, cudaStream_t st, int K, const int* bs, const int* rs, const int* ci,
+                 const T* in, T* out) {
+  auto kern = ogs_pipe_kernel<T, OP, MODE, SPN_OGS_THREADS>;
+  constexpr size_t smem = ogs_pipe_smem_bytes<T, MODE>();
+  static int resident[64];  // CTAs per device, 0 = not yet queried
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (resident[dev] == 0) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SPN_OGS_THREADS, smem);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    resident[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+  }
+  const int NB = (int)grid.x;
+  const dim3 pgrid(NB < resident[dev] ? NB : resident[dev], grid.y);
+  kern<<<pgrid, SPN_OGS_THREADS, smem, st>>>(NB, K, bs, rs, ci, in, out);
+}
+
 template <typename T, int OP>
 void launch_gather(dim3 grid, cudaStream_t st, int K, const int* bs, const int* rs, const int* ci,
                    const void* v, void* gv) {
-  gather_kernel<T, OP><<<grid, kOgsBlock, 0, st>>>(K, bs, rs, ci, static_cast<const T*>(v), static_cast<T*>(gv));
+  launch_pipe<T, OP, OGS_GATHER>(grid, st, K, bs, rs, ci, static_cast<const T*>(v), static_cast<T*>(gv));
 }
 
 template <typename T>
@@ -30,7 +59,7 @@ template <typename T, int OP>
 void launch_gs(dim3 grid, cudaStream_t st, int K, const int* bs, const int* grs, const int* gci,
                const int* srs, const int* sci, void* v) {
   if (grs == srs && gci == sci)
-    gather_scatter_sym_kernel<T, OP><<<grid, kOgsBlock, 0, st>>>(K, bs, grs, gci, static_cast<T*>(v));
+    launch_pipe<T, OP, OGS_GATHER_SCATTER>(grid, st, K, bs, grs, gci, static_cast<const T*>(v), static_cast<T*>(v));
   else
     gather_scatter_kernel<T, OP><<<grid, kOgsBlock, 0, st>>>(K, bs, grs, gci, srs, sci, static_cast<T*>(v));
 }
@@ -96,12 +125,12 @@ int spn_ogs_scatter(int NrowBlocks, int K, const int* blockRowStarts, const int*
   switch (type) {
     case SPN_FLOAT:
     case SPN_INT32:
-      scatter_kernel<unsigned int><<<grid, kOgsBlock, 0, st>>>(K, blockRowStarts, rowStarts, colIds,
+      launch_pipe<unsigned int, SPN_ADD, OGS_SCATTER>(grid, st, K, blockRowStarts, rowStarts, colIds,
           static_cast<const unsigned int*>(gv), static_cast<unsigned int*>(v));
       break;
     case SPN_DOUBLE:
     case SPN_INT64:
-      scatter_kernel<unsigned long long><<<grid, kOgsBlock, 0, st>>>(K, blockRowStarts, rowStarts, colIds,
+      launch_pipe<unsigned long long, SPN_ADD, OGS_SCATTER>(grid, st, K, blockRowStarts, rowStarts, colIds,
           static_cast<const unsigned long long*>(gv), static_cast<unsigned long long*>(v));
       break;
     default: return SPN_ERR_INVALID_ARGUMENT;

@@ -25,8 +25,11 @@
 
 namespace spn {
 
+#ifndef SPN_OGS_NNZB
+#define SPN_OGS_NNZB 2048
+#endif
 static constexpr int kOgsBlock = 256;
-static constexpr int kNodesPerBlock = 2048;
+static constexpr int kNodesPerBlock = SPN_OGS_NNZB;
 // 128-bit index vectors per thread: the block's nnz range is widened down to a
 // multiple of 4, so up to kNodesPerBlock/4+1 vectors are needed.
 static constexpr int kIdxIter = kNodesPerBlock / (4 * kOgsBlock) + 1;

@@ -1,0 +1,254 @@
+// Tile-plan entry points of include/spn_b200.h (spn_ogs_plan_*): the B200-native form of
+// the reference's device operator (ogsOperator_t: libs/ogs/ogsOperator.cpp:597-665 uploads
+// rowStarts/colIds/blockRowStarts; here the row partition is a warp-tile plan, see
+// ogs_tile.cuh) and its three kernels (libs/ogs/ogsOperator.cpp:176-204,295-322,442-481).
+#include <algorithm>
+#include <new>
+#include <vector>
+#include "ogs_tile.cuh"
+
+// Launch geometry per operation, from the sweep in profiles/round1_notes.md (B200, degree-7 hex):
+// U = tiles a warp keeps in flight, MINB = resident 256-thread CTAs per SM the register
+// allocator must allow.  -DSPN_TILE_U / -DSPN_TILE_MINB override all three for sweeps.
+#ifndef SPN_TILE_THREADS
+#define SPN_TILE_THREADS 256
+#endif
+#ifdef SPN_TILE_U
+#define SPN_TILE_U_G SPN_TILE_U
+#define SPN_TILE_U_S SPN_TILE_U
+#define SPN_TILE_U_GS SPN_TILE_U
+#else
+#define SPN_TILE_U_G 3
+#define SPN_TILE_U_S 8
+#define SPN_TILE_U_GS 6
+#endif
+#ifdef SPN_TILE_MINB
+#define SPN_TILE_MINB_G SPN_TILE_MINB
+#define SPN_TILE_MINB_S SPN_TILE_MINB
+#define SPN_TILE_MINB_GS SPN_TILE_MINB
+#else
+#define SPN_TILE_MINB_G 6
+#define SPN_TILE_MINB_S 3
+#define SPN_TILE_MINB_GS 3
+#endif
+
+template <int MODE> struct TileGeom;
+template <> struct TileGeom<spn::TILE_GATHER> { static constexpr int U = SPN_TILE_U_G, MINB = SPN_TILE_MINB_G; };
+template <> struct TileGeom<spn::TILE_SCATTER> { static constexpr int U = SPN_TILE_U_S, MINB = SPN_TILE_MINB_S; };
+template <> struct TileGeom<spn::TILE_GATHER_SCATTER> { static constexpr int U = SPN_TILE_U_GS, MINB = SPN_TILE_MINB_GS; };
+
+using namespace spn;
+
+struct spn_ogs_plan {
+  int Nrows;
+  int NT;    // tiles
+  int nIrr;  // irregular rows
+  long long nnz;
+  unsigned* d_colP;  // packed ids, one 128-byte line per tile (owned)
+  int* d_row0;       // first row of each tile (owned)
+  int* d_irr;        // irregular rows (owned)
+  const int* d_rowStarts;  // borrowed
+  const int* d_colIds;     // borrowed
+};
+
+namespace {
+
+int g_variant = 0;  // experiment knob, see spn_debug_set
+
+template <typename T, int OP, int MODE, int VAR>
+void launch_variant(int grid, cudaStream_t st, const spn_ogs_plan* p, const void* in, void* out) {
+  ogs_tile_kernel<T, OP, MODE, TileGeom<MODE>::U, true, SPN_TILE_THREADS, TileGeom<MODE>::MINB, VAR>
+      <<<grid, SPN_TILE_THREADS, 0, st>>>(p->NT, 1, p->d_colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+}
+
+template <typename T, int OP, int MODE>
+int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaStream_t st) {
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  if (p->NT > 0) {
+    constexpr int U = TileGeom<MODE>::U, TH = SPN_TILE_THREADS, MB = TileGeom<MODE>::MINB;
+    static int resident_kone = 0, resident_k = 0;  // CTAs per SM (same for every sm_100 device)
+    const int warps_needed = (p->NT + U - 1) / U;
+    const int ctas_needed = (warps_needed + TH / 32 - 1) / (TH / 32);
+    if (K == 1) {
+      auto kern = ogs_tile_kernel<T, OP, MODE, U, true, TH, MB>;
+      if (!resident_kone) {
+        int per_sm = 0;
+        SPN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TH, 0));
+        resident_kone = per_sm > 0 ? per_sm : 1;
+      }
+      const int grid = std::min(ctas_needed, resident_kone * d->sms);
+      if (g_variant && sizeof(T) == 8 && OP == SPN_ADD && MODE == TILE_GATHER_SCATTER) {
+        switch (g_variant) {
+          case 2: launch_variant<T, OP, MODE, 2>(grid, st, p, in, out); break;
+          case 4: launch_variant<T, OP, MODE, 4>(grid, st, p, in, out); break;
+          case 6: launch_variant<T, OP, MODE, 6>(grid, st, p, in, out); break;
+          default: return SPN_ERR_INVALID_ARGUMENT;
+        }
+      } else
+      kern<<<grid, TH, 0, st>>>(p->NT, K, p->d_colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+    } else {
+      auto kern = ogs_tile_kernel<T, OP, MODE, U, false, TH, MB>;
+      if (!resident_k) {
+        int per_sm = 0;
+        SPN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TH, 0));
+        resident_k = per_sm > 0 ? per_sm : 1;
+      }
+      const int grid = std::min(ctas_needed, resident_k * d->sms);
+      kern<<<grid, TH, 0, st>>>(p->NT, K, p->d_colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+    }
+    SPN_LAUNCH_CHECK();
+  }
+  if (p->nIrr > 0) {
+    ogs_irregular_kernel<T, OP, MODE><<<(p->nIrr + 127) / 128, 128, 0, st>>>(
+        p->nIrr, K, p->d_irr, p->d_rowStarts, p->d_colIds, static_cast<const T*>(in), static_cast<T*>(out));
+    SPN_LAUNCH_CHECK();
+  }
+  return SPN_SUCCESS;
+}
+
+template <typename T, int MODE>
+int dispatch_op(const spn_ogs_plan* p, int K, const void* in, void* out, int op, cudaStream_t st) {
+  switch (op) {
+    case SPN_ADD: return launch_tiles<T, SPN_ADD, MODE>(p, K, in, out, st);
+    case SPN_MUL: return launch_tiles<T, SPN_MUL, MODE>(p, K, in, out, st);
+    case SPN_MAX: return launch_tiles<T, SPN_MAX, MODE>(p, K, in, out, st);
+    case SPN_MIN: return launch_tiles<T, SPN_MIN, MODE>(p, K, in, out, st);
+    default: return SPN_ERR_INVALID_ARGUMENT;
+  }
+}
+
+template <int MODE>
+int dispatch_type(const spn_ogs_plan* p, int K, const void* in, void* out, int type, int op, cudaStream_t st) {
+  switch (type) {
+    case SPN_FLOAT: return dispatch_op<float, MODE>(p, K, in, out, op, st);
+    case SPN_DOUBLE: return dispatch_op<double, MODE>(p, K, in, out, op, st);
+    case SPN_INT32: return dispatch_op<int, MODE>(p, K, in, out, op, st);
+    case SPN_INT64: return dispatch_op<long long, MODE>(p, K, in, out, op, st);
+    default: return SPN_ERR_INVALID_ARGUMENT;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, const int* h_rowStarts, const int* d_rowStarts,
+                        const int* d_colIds) {
+  if (!plan || Nrows < 0 || (Nrows > 0 && (!h_rowStarts || !d_rowStarts || !d_colIds))) return SPN_ERR_INVALID_ARGUMENT;
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  spn_ogs_plan* p = new (std::nothrow) spn_ogs_plan();
+  if (!p) return SPN_ERR_INVALID_ARGUMENT;
+  p->Nrows = Nrows;
+  p->nnz = Nrows ? (long long)h_rowStarts[Nrows] - h_rowStarts[0] : 0;
+  p->d_rowStarts = d_rowStarts;
+  p->d_colIds = d_colIds;
+  p->d_colP = nullptr;
+  p->d_row0 = nullptr;
+  p->d_irr = nullptr;
+
+  // greedy packing of whole consecutive rows into <=32-nnz tiles
+  std::vector<OgsTileDesc> tiles;
+  std::vector<int> irr;
+  tiles.reserve((size_t)(p->nnz / 24) + 16);
+  OgsTileDesc cur;
+  int cur_n = 0;
+  auto flush = [&]() {
+    if (cur_n > 0) tiles.push_back(cur);
+    cur_n = 0;
+  };
+  for (int r = 0; r < Nrows; ++r) {
+    const int s = h_rowStarts[r], len = h_rowStarts[r + 1] - s;
+    if (len < 0) { delete p; return SPN_ERR_INVALID_ARGUMENT; }
+    if (len == 0 || len > 32) {
+      flush();
+      irr.push_back(r);
+      continue;
+    }
+    if (cur_n + len > 32) flush();
+    if (cur_n == 0) {
+      cur.start = s;
+      cur.row0 = r;
+      cur.last = 0u;
+    }
+    cur_n += len;
+    cur.last |= 1u << (cur_n - 1);
+  }
+  flush();
+  p->NT = (int)tiles.size();
+  p->nIrr = (int)irr.size();
+  if (p->NT) {
+    // re-lay the ids out as one 128-byte line per tile (device side; the descriptors are scratch)
+    OgsTileDesc* d_desc = nullptr;
+    SPN_CUDA_TRY(cudaMalloc(&d_desc, sizeof(OgsTileDesc) * tiles.size()));
+    SPN_CUDA_TRY(cudaMemcpy(d_desc, tiles.data(), sizeof(OgsTileDesc) * tiles.size(), cudaMemcpyHostToDevice));
+    SPN_CUDA_TRY(cudaMalloc(&p->d_colP, sizeof(unsigned) * 32 * tiles.size()));
+    SPN_CUDA_TRY(cudaMalloc(&p->d_row0, sizeof(int) * tiles.size()));
+    const long long blocks = ((long long)p->NT * 32 + 255) / 256;
+    ogs_pack_tiles_kernel<<<(unsigned)blocks, 256>>>(p->NT, d_desc, d_colIds, p->d_colP, p->d_row0);
+    SPN_LAUNCH_CHECK();
+    SPN_CUDA_TRY(cudaDeviceSynchronize());
+    SPN_CUDA_TRY(cudaFree(d_desc));
+  }
+  if (p->nIrr) {
+    SPN_CUDA_TRY(cudaMalloc(&p->d_irr, sizeof(int) * irr.size()));
+    SPN_CUDA_TRY(cudaMemcpy(p->d_irr, irr.data(), sizeof(int) * irr.size(), cudaMemcpyHostToDevice));
+  }
+  *plan = p;
+  return SPN_SUCCESS;
+}
+
+int spn_ogs_plan_destroy(spn_ogs_plan_t plan) {
+  if (!plan) return SPN_SUCCESS;
+  if (plan->d_colP) cudaFree(plan->d_colP);
+  if (plan->d_row0) cudaFree(plan->d_row0);
+  if (plan->d_irr) cudaFree(plan->d_irr);
+  delete plan;
+  return SPN_SUCCESS;
+}
+
+int spn_ogs_plan_info(spn_ogs_plan_t plan, int* Ntiles, int* Nirregular, size_t* plan_bytes) {
+  if (!plan) return SPN_ERR_INVALID_ARGUMENT;
+  if (Ntiles) *Ntiles = plan->NT;
+  if (Nirregular) *Nirregular = plan->nIrr;
+  if (plan_bytes) *plan_bytes = (sizeof(unsigned) * 32 + sizeof(int)) * (size_t)plan->NT + sizeof(int) * (size_t)plan->nIrr;
+  return SPN_SUCCESS;
+}
+
+int spn_ogs_plan_gather(spn_ogs_plan_t plan, int K, const void* v, void* gv, int type, int op, spn_stream_t stream) {
+  if (!plan || K < 1) return SPN_ERR_INVALID_ARGUMENT;
+  if (plan->Nrows == 0) return SPN_SUCCESS;
+  if (!v || !gv) return SPN_ERR_INVALID_ARGUMENT;
+  return dispatch_type<TILE_GATHER>(plan, K, v, gv, type, op, as_stream(stream));
+}
+
+int spn_ogs_plan_scatter(spn_ogs_plan_t plan, int K, const void* gv, void* v, int type, spn_stream_t stream) {
+  if (!plan || K < 1) return SPN_ERR_INVALID_ARGUMENT;
+  if (plan->Nrows == 0) return SPN_SUCCESS;
+  if (!v || !gv) return SPN_ERR_INVALID_ARGUMENT;
+  return dispatch_type<TILE_SCATTER>(plan, K, gv, v, type, SPN_ADD, as_stream(stream));
+}
+
+int spn_debug_set(int key, int value) {
+  if (key == 0) { g_variant = value; return SPN_SUCCESS; }
+  return SPN_ERR_INVALID_ARGUMENT;
+}
+
+int spn_ogs_plan_gather_scatter_to(spn_ogs_plan_t plan, int K, const void* v, void* w, int type, int op, spn_stream_t stream) {
+  if (!plan || K < 1) return SPN_ERR_INVALID_ARGUMENT;
+  if (plan->Nrows == 0) return SPN_SUCCESS;
+  if (!v || !w) return SPN_ERR_INVALID_ARGUMENT;
+  return dispatch_type<TILE_GATHER_SCATTER>(plan, K, v, w, type, op, as_stream(stream));
+}
+
+int spn_ogs_plan_gather_scatter(spn_ogs_plan_t plan, int K, void* v, int type, int op, spn_stream_t stream) {
+  if (!plan || K < 1) return SPN_ERR_INVALID_ARGUMENT;
+  if (plan->Nrows == 0) return SPN_SUCCESS;
+  if (!v) return SPN_ERR_INVALID_ARGUMENT;
+  return dispatch_type<TILE_GATHER_SCATTER>(plan, K, v, v, type, op, as_stream(stream));
+}
+
+}  // extern "C"

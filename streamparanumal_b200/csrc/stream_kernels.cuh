@@ -17,7 +17,7 @@ namespace spn {
 // ---------------------------------------------------------------------------
 // reduction workspace: [counter | pad to 128 B | partials[kMaxPartials]]
 // ---------------------------------------------------------------------------
-static constexpr int kMaxPartials = 4096;
+static constexpr int kMaxPartials = 65536;
 struct ReduceWs {
   unsigned int counter;
   unsigned int pad[31];

@@ -141,3 +141,55 @@ def ogs_extract(N, K, ids, q, out):
         return
     check(_lib.kernel_lib().spn_ogs_extract(int(N), int(K), _dev(ids, torch.int32), _dev(q), _dev(out),
                                             ogs_type(q), _stream()), "ogs extract")
+
+
+# ---- ogs operator plan (warp-tile form of ogsOperator_t) --------------------------
+class OgsPlan:
+    """Device operator built once from the host rowStarts (reference: ogsOperator_t ctor,
+    libs/ogs/ogsOperator.cpp:597-665).  rowStarts is a host int32 array; d_rowStarts /
+    d_colIds are the device copies (kept alive by this object)."""
+
+    def __init__(self, rowStarts, d_rowStarts, d_colIds):
+        import ctypes
+        import numpy as np
+        rs = np.ascontiguousarray(rowStarts, dtype=np.int32)
+        self.Nrows = rs.size - 1
+        self._keep = (d_rowStarts, d_colIds)
+        self._h = ctypes.c_void_p()
+        check(_lib.kernel_lib().spn_ogs_plan_create(ctypes.byref(self._h), self.Nrows, rs.ctypes.data,
+                                                    _dev(d_rowStarts, torch.int32), _dev(d_colIds, torch.int32)),
+              "ogs plan create")
+        nt, nirr, nbytes = ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+        check(_lib.kernel_lib().spn_ogs_plan_info(self._h, ctypes.byref(nt), ctypes.byref(nirr), ctypes.byref(nbytes)))
+        self.Ntiles, self.Nirregular, self.plan_bytes = nt.value, nirr.value, nbytes.value
+
+    def gather(self, K, v, gv, op=ADD):
+        if gv.dtype != v.dtype:
+            raise TypeError("v and gv must have the same dtype")
+        check(_lib.kernel_lib().spn_ogs_plan_gather(self._h, int(K), _dev(v), _dev(gv), ogs_type(v), int(op), _stream()),
+              "ogs plan gather")
+
+    def scatter(self, K, gv, v):
+        if gv.dtype != v.dtype:
+            raise TypeError("v and gv must have the same dtype")
+        check(_lib.kernel_lib().spn_ogs_plan_scatter(self._h, int(K), _dev(gv), _dev(v), ogs_type(v), _stream()),
+              "ogs plan scatter")
+
+    def gather_scatter(self, K, v, op=ADD):
+        check(_lib.kernel_lib().spn_ogs_plan_gather_scatter(self._h, int(K), _dev(v), ogs_type(v), int(op), _stream()),
+              "ogs plan gatherScatter")
+
+    def gather_scatter_to(self, K, v, w, op=ADD):
+        check(_lib.kernel_lib().spn_ogs_plan_gather_scatter_to(self._h, int(K), _dev(v), _dev(w), ogs_type(v), int(op),
+                                                               _stream()), "ogs plan gatherScatter (out of place)")
+
+    def close(self):
+        if self._h:
+            _lib.kernel_lib().spn_ogs_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -184,6 +184,7 @@ def test_ogs_kernels_bit_exact(K, oracle, dtype, Kv, npb):
         bs = oracle.block_rows(rs, limit) if npb == 512 else util.greedy_blocks(rs, limit)
         nb = bs.size - 1
         d_bs, d_rs, d_ci = dev(bs), dev(rs), dev(ci)
+        plan = K.OgsPlan(rs, d_rs, d_ci)
         v = _values(ids.size * Kv, dtype, 20 + m)
         for op in _ops_for(dtype):
             if op == 1 and not np.issubdtype(dtype, np.floating):
@@ -198,10 +199,20 @@ def test_ogs_kernels_bit_exact(K, oracle, dtype, Kv, npb):
             dq = dev(vv)
             K.ogs_gather_scatter(nb, Kv, d_bs, d_rs, d_ci, d_rs, d_ci, dq, op=op)
             assert np.array_equal(dq.cpu().numpy(), oracle.ogs_gather_scatter(rs, ci, rs, ci, vv, K=Kv, op=op)), (mesh, op)
+            # the same three operations through the warp-tile plan
+            dgv.zero_()
+            plan.gather(Kv, dv, dgv, op=op)
+            assert np.array_equal(dgv.cpu().numpy(), g_ref), ("plan", mesh, op)
+            dq = dev(vv)
+            plan.gather_scatter(Kv, dq, op=op)
+            assert np.array_equal(dq.cpu().numpy(), oracle.ogs_gather_scatter(rs, ci, rs, ci, vv, K=Kv, op=op)), ("plan", mesh, op)
         dv = dev(v)
         g = oracle.ogs_gather(rs, ci, v, K=Kv, op=0)
         dout = torch.zeros_like(dv)
         K.ogs_scatter(nb, Kv, d_bs, d_rs, d_ci, dev(g), dout)
+        assert np.array_equal(dout.cpu().numpy(), oracle.ogs_scatter(rs, ci, g, np.zeros_like(v), K=Kv))
+        dout.zero_()
+        plan.scatter(Kv, dev(g), dout)
         assert np.array_equal(dout.cpu().numpy(), oracle.ogs_scatter(rs, ci, g, np.zeros_like(v), K=Kv))
         pick = ((np.arange(1 + ids.size // 3) * 31) % ids.size).astype(np.int32)
         dext = torch.empty(pick.size * Kv, dtype=dv.dtype, device="cuda")
@@ -253,6 +264,19 @@ def test_ogs_high_multiplicity_and_masked_nodes(K, oracle):
     dout = torch.full((n,), -1.0, dtype=torch.float64, device="cuda")
     K.ogs_scatter(nb, 1, dev(bs), dev(rs), dev(ci), dgv, dout)
     assert np.array_equal(dout.cpu().numpy(), oracle.ogs_scatter(rs, ci, dgv.cpu().numpy(), np.full(n, -1.0)))
+    # warp-tile plan: the long rows (> 32) go through the irregular-row kernel
+    d_rs, d_ci = dev(rs), dev(ci)
+    plan = K.OgsPlan(rs, d_rs, d_ci)
+    assert plan.Nirregular >= 2
+    g2 = torch.zeros_like(dgv)
+    plan.gather(1, dv, g2)
+    assert np.array_equal(g2.cpu().numpy(), oracle.ogs_gather(rs, ci, v))
+    dq = dev(v)
+    plan.gather_scatter(1, dq)
+    assert np.array_equal(dq.cpu().numpy(), ref)
+    dout = torch.full((n,), -1.0, dtype=torch.float64, device="cuda")
+    plan.scatter(1, g2, dout)
+    assert np.array_equal(dout.cpu().numpy(), oracle.ogs_scatter(rs, ci, g2.cpu().numpy(), np.full(n, -1.0)))
 
 
 def test_ogs_properties_at_scale(K):

@@ -29,7 +29,7 @@ def timeit(fn, iters=20, warm=5):
 def main():
     nx = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     p = int(sys.argv[2]) if len(sys.argv) > 2 else 7
-    limits = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [K.nodes_per_block(), 1024, 512]
+    limits = [K.nodes_per_block() if x == "native" else int(x) for x in sys.argv[3].split(",") if x != "none"] if len(sys.argv) > 3 else [K.nodes_per_block(), 1024, 512]
     t0 = time.time()
     ids = util.hex_ids(nx, nx, nx, p)
     rs, ci = util.csr_from_ids(ids)
@@ -41,6 +41,26 @@ def main():
     gv = torch.empty(Ng, dtype=torch.float64, device="cuda")
     b6 = 4 * (Ng + 1) + 4 * Nt + 8 * Nt + 8 * Ng
     b8 = 4 * (Ng + 1) + 4 * Nt + 16 * Nt
+    t0 = time.time()
+    plan = K.OgsPlan(rs, d_rs, d_ci)
+    print(f"plan: {plan.Ntiles} tiles ({Nt / max(plan.Ntiles, 1):.1f} nnz/tile), {plan.Nirregular} irregular rows, "
+          f"{plan.plan_bytes / 1e6:.1f} MB, built in {time.time() - t0:.2f}s", flush=True)
+    tg = timeit(lambda: plan.gather(1, v, gv))
+    ts = timeit(lambda: plan.scatter(1, gv, v))
+    tgs = timeit(lambda: plan.gather_scatter(1, v), iters=50)
+    print(f"tile plan: gather {tg*1e3:.3f} ms {b6/tg*1e-9:7.1f} GB/s | scatter {ts*1e3:.3f} ms {b6/ts*1e-9:7.1f} GB/s | "
+          f"gatherScatter {tgs*1e3:.3f} ms {b8/tgs*1e-9:7.1f} GB/s {Ng/tgs*1e-9:6.1f} GDOF/s", flush=True)
+    if os.environ.get("OGS_PROBE"):
+        from streamparanumal_b200 import _lib
+        w = torch.empty_like(v)
+        t = timeit(lambda: plan.gather_scatter_to(1, v, w), iters=50)
+        print(f"probe out-of-place gs: {t*1e3:.3f} ms {b8/t*1e-9:7.1f} GB/s", flush=True)
+        for var in (2, 4, 6):
+            _lib.kernel_lib().spn_debug_set(0, var)
+            t = timeit(lambda: plan.gather_scatter(1, v), iters=50)
+            t2 = timeit(lambda: plan.gather_scatter_to(1, v, w), iters=50)
+            print(f"probe variant {var}: in-place {t*1e3:.3f} ms {b8/t*1e-9:7.1f} GB/s | out-of-place {t2*1e3:.3f} ms", flush=True)
+        _lib.kernel_lib().spn_debug_set(0, 0)
     for lim in limits:
         bs = util.greedy_blocks(rs, lim)
         nb = bs.size - 1
