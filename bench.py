@@ -232,10 +232,10 @@ def run_suite(torch, K, peak, ogs_ctx):
     out["BS0 launch"] = {"us_per_launch": (time.perf_counter() - t0) / 1000 * 1e6}
     del Ap, r
     # BS6 / BS7 on the headline mesh
-    nb, d_bs, d_rs, d_ci, Nt, Ng, q = ogs_ctx
+    plan, Nt, Ng, q = ogs_ctx
     gq = torch.empty(Ng, dtype=torch.float64, device=dev)
-    add("BS6 gather", bs6_bytes(Nt, Ng), cuda_time(lambda: K.ogs_gather(nb, 1, d_bs, d_rs, d_ci, q, gq), 20, 5, torch), Ng)
-    add("BS7 scatter", bs6_bytes(Nt, Ng), cuda_time(lambda: K.ogs_scatter(nb, 1, d_bs, d_rs, d_ci, gq, q), 20, 5, torch), Ng)
+    add("BS6 gather", bs6_bytes(Nt, Ng), cuda_time(lambda: plan.gather(1, q, gq), 20, 5, torch), Ng)
+    add("BS7 scatter", bs6_bytes(Nt, Ng), cuda_time(lambda: plan.scatter(1, gq, q), 20, 5, torch), Ng)
     return out
 
 
@@ -267,16 +267,16 @@ def run_b200(args):
     ids = util.hex_ids(nx, nx, nx, p)
     rs, ci = util.csr_from_ids(ids)
     del ids
-    bs = util.greedy_blocks(rs, K.nodes_per_block())
-    Nt, Ng, nb = ci.size, rs.size - 1, bs.size - 1
+    Nt, Ng = ci.size, rs.size - 1
+    d_rs, d_ci = (torch.from_numpy(x).cuda() for x in (rs, ci))
+    plan = K.OgsPlan(rs, d_rs, d_ci, Nt)  # device operator (ogsOperator_t ctor equivalent)
     t_setup = time.perf_counter() - t_setup
-    d_bs, d_rs, d_ci = (torch.from_numpy(x).cuda() for x in (bs, rs, ci))
     q = torch.from_numpy(util.splitmix64(Nt, 3 + rank)).cuda()
 
     if world > 1:
         raise SystemExit("multi-GPU BS8 (halo exchange) is not wired into bench.py yet")
 
-    step = lambda: K.ogs_gather_scatter(nb, 1, d_bs, d_rs, d_ci, d_rs, d_ci, q)
+    step = lambda: plan.gather_scatter(1, q)
 
     # ---- timed region: device-resident ----
     for _ in range(args.warmup):
@@ -321,11 +321,11 @@ def run_b200(args):
         "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"BS8 ogs gatherScatter(Add,Sym,K=1), hex p={p}, {nx}^3 elements per rank",
-                   "nx": nx, "p": p, "Nt_per_rank": Nt, "Ng_per_rank": Ng, "row_blocks": nb,
+                   "nx": nx, "p": p, "Nt_per_rank": Nt, "Ng_per_rank": Ng, "tiles": plan.Ntiles,
                    "l2": "q (1.07 GB) + CSR (0.9 GB) per call exceed the 126 MB L2; no flush needed",
                    "host_setup_s": round(t_setup, 2)},
         "effective_gbs": bs8_bytes(Nt, Ng) * world / t_step * 1e-9,
-        "roofline": {"bound": "hbm", "kernel": "gather_scatter_sym_kernel<double,Add>",
+        "roofline": {"bound": "hbm", "kernel": "ogs_tile_kernel<double,Add,GATHER_SCATTER>",
                      "achieved": bs8_bytes(Nt, Ng) / t_step * 1e-9, "peak": peak, "peak_source": peak_src,
                      "unit": "GB/s", "frac": bs8_bytes(Nt, Ng) / t_step * 1e-9 / peak,
                      "frac_of_8TBs_nominal": bs8_bytes(Nt, Ng) / t_step * 1e-9 / 8000.0,
@@ -337,7 +337,7 @@ def run_b200(args):
     }
 
     if args.suite and world == 1:
-        line["suite"] = run_suite(torch, K, peak, (nb, d_bs, d_rs, d_ci, Nt, Ng, q))
+        line["suite"] = run_suite(torch, K, peak, (plan, Nt, Ng, q))
         line["suite"]["BS8 gatherScatter"] = {"ms": t_step * 1e3, "GB/s": line["effective_gbs"],
                                               "frac_of_measured_peak": line["roofline"]["frac"],
                                               "frac_of_8TBs": line["roofline"]["frac_of_8TBs_nominal"],

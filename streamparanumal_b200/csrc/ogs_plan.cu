@@ -47,6 +47,8 @@ struct spn_ogs_plan {
   unsigned* d_colP;  // packed ids, one 128-byte line per tile (owned)
   int* d_row0;       // first row of each tile (owned)
   int* d_irr;        // irregular rows (owned)
+  int* d_rowOf;      // row of every column, -1 = none (owned); drives scatter
+  long long Ncols;
   const int* d_rowStarts;  // borrowed
   const int* d_colIds;     // borrowed
 };
@@ -134,9 +136,10 @@ int dispatch_type(const spn_ogs_plan* p, int K, const void* in, void* out, int t
 
 extern "C" {
 
-int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, const int* h_rowStarts, const int* d_rowStarts,
+int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h_rowStarts, const int* d_rowStarts,
                         const int* d_colIds) {
-  if (!plan || Nrows < 0 || (Nrows > 0 && (!h_rowStarts || !d_rowStarts || !d_colIds))) return SPN_ERR_INVALID_ARGUMENT;
+  if (!plan || Nrows < 0 || Ncols < 0 || (Nrows > 0 && (!h_rowStarts || !d_rowStarts || !d_colIds)))
+    return SPN_ERR_INVALID_ARGUMENT;
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
@@ -149,6 +152,8 @@ int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, const int* h_rowStarts,
   p->d_colP = nullptr;
   p->d_row0 = nullptr;
   p->d_irr = nullptr;
+  p->d_rowOf = nullptr;
+  p->Ncols = Ncols;
 
   // greedy packing of whole consecutive rows into <=32-nnz tiles
   std::vector<OgsTileDesc> tiles;
@@ -185,9 +190,9 @@ int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, const int* h_rowStarts,
     OgsTileDesc* d_desc = nullptr;
     SPN_CUDA_TRY(cudaMalloc(&d_desc, sizeof(OgsTileDesc) * tiles.size()));
     SPN_CUDA_TRY(cudaMemcpy(d_desc, tiles.data(), sizeof(OgsTileDesc) * tiles.size(), cudaMemcpyHostToDevice));
-    SPN_CUDA_TRY(cudaMalloc(&p->d_colP, sizeof(unsigned) * 32 * tiles.size()));
-    SPN_CUDA_TRY(cudaMalloc(&p->d_row0, sizeof(int) * tiles.size()));
-    const long long blocks = ((long long)p->NT * 32 + 255) / 256;
+    SPN_CUDA_TRY(cudaMalloc(&p->d_colP, sizeof(unsigned) * 32 * (tiles.size() + kTilePad)));
+    SPN_CUDA_TRY(cudaMalloc(&p->d_row0, sizeof(int) * (tiles.size() + kTilePad)));
+    const long long blocks = (((long long)p->NT + kTilePad) * 32 + 255) / 256;
     ogs_pack_tiles_kernel<<<(unsigned)blocks, 256>>>(p->NT, d_desc, d_colIds, p->d_colP, p->d_row0);
     SPN_LAUNCH_CHECK();
     SPN_CUDA_TRY(cudaDeviceSynchronize());
@@ -197,6 +202,21 @@ int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, const int* h_rowStarts,
     SPN_CUDA_TRY(cudaMalloc(&p->d_irr, sizeof(int) * irr.size()));
     SPN_CUDA_TRY(cudaMemcpy(p->d_irr, irr.data(), sizeof(int) * irr.size(), cudaMemcpyHostToDevice));
   }
+  if (Ncols > 0) {
+    // inverse map for scatter: rowOf[c] = row holding column c, -1 if none
+    SPN_CUDA_TRY(cudaMalloc(&p->d_rowOf, sizeof(int) * (size_t)Ncols));
+    SPN_CUDA_TRY(cudaMemset(p->d_rowOf, 0xff, sizeof(int) * (size_t)Ncols));
+    if (p->NT) {
+      const long long blocks = ((long long)p->NT * 32 + 255) / 256;
+      ogs_build_rowof_kernel<<<(unsigned)blocks, 256>>>(p->NT, p->d_colP, p->d_row0, p->d_rowOf);
+      SPN_LAUNCH_CHECK();
+    }
+    if (p->nIrr) {
+      ogs_build_rowof_irregular_kernel<<<(p->nIrr + 127) / 128, 128>>>(p->nIrr, p->d_irr, d_rowStarts, d_colIds, p->d_rowOf);
+      SPN_LAUNCH_CHECK();
+    }
+    SPN_CUDA_TRY(cudaDeviceSynchronize());
+  }
   *plan = p;
   return SPN_SUCCESS;
 }
@@ -205,6 +225,7 @@ int spn_ogs_plan_destroy(spn_ogs_plan_t plan) {
   if (!plan) return SPN_SUCCESS;
   if (plan->d_colP) cudaFree(plan->d_colP);
   if (plan->d_row0) cudaFree(plan->d_row0);
+  if (plan->d_rowOf) cudaFree(plan->d_rowOf);
   if (plan->d_irr) cudaFree(plan->d_irr);
   delete plan;
   return SPN_SUCCESS;
@@ -214,7 +235,9 @@ int spn_ogs_plan_info(spn_ogs_plan_t plan, int* Ntiles, int* Nirregular, size_t*
   if (!plan) return SPN_ERR_INVALID_ARGUMENT;
   if (Ntiles) *Ntiles = plan->NT;
   if (Nirregular) *Nirregular = plan->nIrr;
-  if (plan_bytes) *plan_bytes = (sizeof(unsigned) * 32 + sizeof(int)) * (size_t)plan->NT + sizeof(int) * (size_t)plan->nIrr;
+  if (plan_bytes)
+    *plan_bytes = (sizeof(unsigned) * 32 + sizeof(int)) * (size_t)(plan->NT + kTilePad) + sizeof(int) * (size_t)plan->nIrr +
+                  sizeof(int) * (size_t)plan->Ncols;
   return SPN_SUCCESS;
 }
 
@@ -229,7 +252,38 @@ int spn_ogs_plan_scatter(spn_ogs_plan_t plan, int K, const void* gv, void* v, in
   if (!plan || K < 1) return SPN_ERR_INVALID_ARGUMENT;
   if (plan->Nrows == 0) return SPN_SUCCESS;
   if (!v || !gv) return SPN_ERR_INVALID_ARGUMENT;
-  return dispatch_type<TILE_SCATTER>(plan, K, gv, v, type, SPN_ADD, as_stream(stream));
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  const int64_t Ncols = plan->Ncols;
+  if (Ncols == 0) return SPN_SUCCESS;
+  const bool wide = (type == SPN_DOUBLE || type == SPN_INT64);
+  if (type != SPN_FLOAT && type != SPN_INT32 && !wide) return SPN_ERR_INVALID_ARGUMENT;
+  if (K == 1) {
+    constexpr int UNR = 2;
+    const uintptr_t vp = reinterpret_cast<uintptr_t>(v), rp = reinterpret_cast<uintptr_t>(plan->d_rowOf);
+    const bool vec = ((vp & (wide ? 31 : 15)) == 0) && ((rp & 15) == 0);
+    const int64_t groups = vec ? Ncols / 4 : Ncols;
+    int64_t grid = (groups + 256 * UNR - 1) / (256 * UNR);
+    grid = std::max<int64_t>(1, std::min<int64_t>(grid, 0x7fffffff));
+    if (wide) {
+      using T = unsigned long long;
+      if (vec) ogs_scatter_cols_kernel<T, 4, UNR><<<(unsigned)grid, 256, 0, st>>>(Ncols, plan->d_rowOf, static_cast<const T*>(gv), static_cast<T*>(v));
+      else ogs_scatter_cols_kernel<T, 1, UNR><<<(unsigned)grid, 256, 0, st>>>(Ncols, plan->d_rowOf, static_cast<const T*>(gv), static_cast<T*>(v));
+    } else {
+      using T = unsigned int;
+      if (vec) ogs_scatter_cols_kernel<T, 4, UNR><<<(unsigned)grid, 256, 0, st>>>(Ncols, plan->d_rowOf, static_cast<const T*>(gv), static_cast<T*>(v));
+      else ogs_scatter_cols_kernel<T, 1, UNR><<<(unsigned)grid, 256, 0, st>>>(Ncols, plan->d_rowOf, static_cast<const T*>(gv), static_cast<T*>(v));
+    }
+  } else {
+    const int64_t total = Ncols * K;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)d->sms * 32));
+    if (wide) ogs_scatter_cols_k_kernel<unsigned long long><<<(unsigned)grid, 256, 0, st>>>(Ncols, K, plan->d_rowOf, static_cast<const unsigned long long*>(gv), static_cast<unsigned long long*>(v));
+    else ogs_scatter_cols_k_kernel<unsigned int><<<(unsigned)grid, 256, 0, st>>>(Ncols, K, plan->d_rowOf, static_cast<const unsigned int*>(gv), static_cast<unsigned int*>(v));
+  }
+  SPN_LAUNCH_CHECK();
+  return SPN_SUCCESS;
 }
 
 int spn_debug_set(int key, int value) {

@@ -26,6 +26,9 @@
 namespace spn {
 
 static constexpr unsigned kEmptyLane = 0xFFFFFFFFu;
+// colP / row0 carry this many all-empty tiles after the last real one, so a warp may load its
+// U consecutive tiles without per-tile bounds checks (U <= kTilePad)
+static constexpr int kTilePad = 16;
 
 // build-time descriptor (host -> pack kernel); not used by the hot kernels
 struct OgsTileDesc {
@@ -41,7 +44,12 @@ ogs_pack_tiles_kernel(int NT, const OgsTileDesc* __restrict__ desc, const int* _
                       unsigned* __restrict__ colP, int* __restrict__ row0) {
   const int lane = threadIdx.x & 31;
   const int64_t t = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
-  if (t >= NT) return;
+  if (t >= NT + kTilePad) return;
+  if (t >= NT) {  // padding tiles
+    colP[32 * t + lane] = kEmptyLane;
+    if (lane == 0) row0[t] = 0;
+    return;
+  }
   const OgsTileDesc d = desc[t];
   const int count = 32 - __clz(d.last);
   unsigned w = kEmptyLane;
@@ -52,6 +60,22 @@ ogs_pack_tiles_kernel(int NT, const OgsTileDesc* __restrict__ desc, const int* _
 
 template <typename T>
 __device__ __forceinline__ T shfl_up1(T x) { return __shfl_up_sync(0xffffffffu, x, 1); }
+
+// one fold round: the lane at position t of its row takes its left neighbour's prefix y and
+// folds its own value.  FP64 Add gets a predicated DADD (the generic form compiles to
+// DADD + two selects).
+template <typename T, int OP>
+__device__ __forceinline__ void fold_step(T& acc, T y, const T x, int pos, int t) {
+  if (pos == t) {
+    OgsOp<T, OP>::apply(y, x);
+    acc = y;
+  }
+}
+template <>
+__device__ __forceinline__ void fold_step<double, SPN_ADD>(double& acc, double y, const double x, int pos, int t) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %3, %4;\n\t@p add.rn.f64 %0, %1, %2;\n\t}"
+      : "+d"(acc) : "d"(y), "d"(x), "r"(pos), "r"(t));
+}
 template <typename T>
 __device__ __forceinline__ T shfl_idx(T x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 
@@ -95,20 +119,23 @@ ogs_tile_kernel(int NT, int K, const unsigned* __restrict__ colP, const int* __r
   int64_t base = (int64_t)warp * U;
   if (base >= NT) return;
 
+  static_assert(U <= kTilePad, "tile padding too small");
   unsigned w[U];
+  int r0[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) w[u] = (base + u < NT) ? ld_ids(colP + 32 * (base + u) + lane) : kEmptyLane;
+  for (int u = 0; u < U; ++u) {
+    w[u] = ld_ids(colP + 32 * (base + u) + lane);
+    r0[u] = (MODE != TILE_GATHER_SCATTER) ? __ldg(row0 + base + u) : 0;
+  }
 
   for (; base < NT; base += step) {
     bool valid[U];
     int col[U];
     unsigned last[U];
-    int r0[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       valid[u] = (w[u] != kEmptyLane);
       col[u] = (int)(w[u] & 0x7fffffffu);
-      if (MODE != TILE_GATHER_SCATTER) r0[u] = (base + u < NT) ? __ldg(row0 + base + u) : 0;
     }
 
     // ---- indexed loads of the current tiles (K == 1)
@@ -120,10 +147,15 @@ ogs_tile_kernel(int NT, int K, const unsigned* __restrict__ colP, const int* __r
 
     // ---- prefetch the id lines of the next U tiles
     unsigned wn[U];
+    int r0n[U];
+    {
+      // clamp instead of branching: the last iteration re-reads its own (cached) lines
+      const int64_t tn = (base + step < NT) ? base + step : base;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t tn = base + step + u;
-      wn[u] = (tn < NT) ? ld_ids(colP + 32 * tn + lane) : kEmptyLane;
+      for (int u = 0; u < U; ++u) {
+        wn[u] = ld_ids(colP + 32 * (tn + u) + lane);
+        r0n[u] = (MODE != TILE_GATHER_SCATTER) ? __ldg(row0 + tn + u) : 0;
+      }
     }
 
     // ---- row structure from the sign bits
@@ -144,7 +176,7 @@ ogs_tile_kernel(int NT, int K, const unsigned* __restrict__ colP, const int* __r
           if (valid[u]) x[u] = __ldg(in + r0[u] + rowidx[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u)
-          if (valid[u]) st_var<VAR, T>(out + col[u], x[u]);
+          if (valid[u]) out[col[u]] = x[u];  // plain: partial sectors must stay in L2 until their neighbours arrive
       } else {
         const int R = __reduce_max_sync(0xffffffffu, maxpos);
         T acc[U];
@@ -156,11 +188,7 @@ ogs_tile_kernel(int NT, int K, const unsigned* __restrict__ colP, const int* __r
         for (int t = 1; t <= R; ++t) {
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            T y = shfl_up1(acc[u]);
-            if (pos[u] == t) {
-              OgsOp<T, OP>::apply(y, x[u]);
-              acc[u] = y;
-            }
+            fold_step<T, OP>(acc[u], shfl_up1(acc[u]), x[u], pos[u], t);
           }
         }
 #pragma unroll
@@ -189,11 +217,7 @@ ogs_tile_kernel(int NT, int K, const unsigned* __restrict__ colP, const int* __r
           T a = OgsOp<T, OP>::init();
           OgsOp<T, OP>::apply(a, xv);
           for (int t = 1; t <= R; ++t) {
-            T y = shfl_up1(a);
-            if (pos[u] == t) {
-              OgsOp<T, OP>::apply(y, xv);
-              a = y;
-            }
+            fold_step<T, OP>(a, shfl_up1(a), xv, pos[u], t);
           }
           if (MODE == TILE_GATHER) {
             if (valid[u] && (w[u] >> 31)) out[k + row * K] = a;
@@ -207,7 +231,110 @@ ogs_tile_kernel(int NT, int K, const unsigned* __restrict__ colP, const int* __r
     }
 
 #pragma unroll
-    for (int u = 0; u < U; ++u) w[u] = wn[u];
+    for (int u = 0; u < U; ++u) {
+      w[u] = wn[u];
+      r0[u] = r0n[u];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// scatter by columns.  Every column belongs to at most one row (the ogs invariant,
+// include/ogs/ogsOperator.hpp:41-43), so v[colIds[g]] = gv[row] for all g is the same
+// as v[c] = gv[rowOf[c]] for every column c that has a row: a pure streaming kernel
+// with fully coalesced 256-bit stores of v and mostly-contiguous reads of gv, instead
+// of indexed 8-byte stores.  rowOf[c] = -1 marks a column outside the operator (left
+// untouched, like the reference).  Index traffic is 4 B per column, what colIds costs.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ogs_build_rowof_kernel(int NT, const unsigned* __restrict__ colP, const int* __restrict__ row0,
+                       int* __restrict__ rowOf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (t >= NT) return;
+  const unsigned w = colP[32 * t + lane];
+  const bool valid = (w != kEmptyLane);
+  const unsigned last = __ballot_sync(0xffffffffu, valid && (w >> 31));
+  const unsigned heads = ((last << 1) | 1u) & (0xffffffffu >> (31 - lane));
+  if (valid) rowOf[w & 0x7fffffffu] = row0[t] + __popc(heads) - 1;
+}
+
+__global__ void __launch_bounds__(128)
+ogs_build_rowof_irregular_kernel(int nIrr, const int* __restrict__ irrRows, const int* __restrict__ rowStarts,
+                                 const int* __restrict__ colIds, int* __restrict__ rowOf) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= nIrr) return;
+  const int row = irrRows[i];
+  for (int g = rowStarts[row]; g < rowStarts[row + 1]; ++g) rowOf[colIds[g]] = row;
+}
+
+// T is an unsigned type of the element size; VEC = columns per thread (4 needs v 32-byte
+// aligned for 8-byte T / 16-byte aligned for 4-byte T, and rowOf 16-byte aligned)
+template <typename T, int VEC, int UNROLL>
+__global__ void __launch_bounds__(256)
+ogs_scatter_cols_kernel(int64_t Ncols, const int* __restrict__ rowOf, const T* __restrict__ gv, T* __restrict__ v) {
+  const int64_t ngroups = Ncols / VEC;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t g0 = (int64_t)blockIdx.x * 256 + threadIdx.x; g0 < ngroups; g0 += stride * UNROLL) {
+    int r[UNROLL][VEC];
+    T x[UNROLL][VEC];
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+      const int64_t g = g0 + j * stride;
+      if (g < ngroups) {
+        if (VEC == 4) {
+          const int4 q = __ldg(reinterpret_cast<const int4*>(rowOf) + g);
+          r[j][0] = q.x; r[j][1] = q.y; r[j][2] = q.z; r[j][3] = q.w;
+        } else {
+          r[j][0] = __ldg(rowOf + g);
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < VEC; ++l) r[j][l] = -1;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j)
+#pragma unroll
+      for (int l = 0; l < VEC; ++l)
+        if (r[j][l] >= 0) x[j][l] = __ldg(gv + r[j][l]);
+#pragma unroll
+    for (int j = 0; j < UNROLL; ++j) {
+      const int64_t g = g0 + j * stride;
+      if (VEC == 4 && (r[j][0] | r[j][1] | r[j][2] | r[j][3]) >= 0) {
+        if (sizeof(T) == 8) {
+          asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(v + 4 * g), "l"((unsigned long long)x[j][0]),
+                       "l"((unsigned long long)x[j][1]), "l"((unsigned long long)x[j][2]), "l"((unsigned long long)x[j][3]) : "memory");
+        } else {
+          asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(v + 4 * g), "r"((unsigned)x[j][0]), "r"((unsigned)x[j][1]),
+                       "r"((unsigned)x[j][2]), "r"((unsigned)x[j][3]) : "memory");
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < VEC; ++l)
+          if (r[j][l] >= 0) v[VEC * g + l] = x[j][l];
+      }
+    }
+  }
+  if (VEC > 1 && blockIdx.x == 0 && threadIdx.x < VEC) {  // tail columns
+    const int64_t c = ngroups * VEC + threadIdx.x;
+    if (c < Ncols) {
+      const int row = rowOf[c];
+      if (row >= 0) v[c] = gv[row];
+    }
+  }
+}
+
+// general K: one thread per (column, k)
+template <typename T>
+__global__ void __launch_bounds__(256)
+ogs_scatter_cols_k_kernel(int64_t Ncols, int K, const int* __restrict__ rowOf, const T* __restrict__ gv, T* __restrict__ v) {
+  const int64_t total = Ncols * K;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t c = i / K;
+    const int k = (int)(i - c * K);
+    const int row = __ldg(rowOf + c);
+    if (row >= 0) v[i] = __ldg(gv + (k + (int64_t)row * K));
   }
 }
 

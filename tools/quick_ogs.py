@@ -42,7 +42,7 @@ def main():
     b6 = 4 * (Ng + 1) + 4 * Nt + 8 * Nt + 8 * Ng
     b8 = 4 * (Ng + 1) + 4 * Nt + 16 * Nt
     t0 = time.time()
-    plan = K.OgsPlan(rs, d_rs, d_ci)
+    plan = K.OgsPlan(rs, d_rs, d_ci, Nt)
     print(f"plan: {plan.Ntiles} tiles ({Nt / max(plan.Ntiles, 1):.1f} nnz/tile), {plan.Nirregular} irregular rows, "
           f"{plan.plan_bytes / 1e6:.1f} MB, built in {time.time() - t0:.2f}s", flush=True)
     tg = timeit(lambda: plan.gather(1, v, gv))
