@@ -173,7 +173,9 @@ int spn_ogs_extract(int N, int K, const int* ids, const void* q, void* gatherq, 
  * colIds + rowStarts + blockRowStarts.  Ncols is the operator's column count
  * (ogsOperator_t::Ncols: every colId < Ncols; vectors v have Ncols*K entries); the plan
  * also stores the inverse map column -> row, which turns Scatter into a streaming
- * kernel with coalesced stores.  d_rowStarts / d_colIds are BORROWED device
+ * kernel with coalesced stores.  h_colIds (host copy of colIds, may be NULL) lets the
+ * plan give GatherScatter its own row order whose indexed stores complete whole
+ * 32-byte sectors; without it GatherScatter walks the Gather tiles.  d_rowStarts / d_colIds are BORROWED device
  * arrays that must outlive the plan.  The three calls are the device Gather /
  * Scatter / GatherScatter of libs/ogs/ogsOperator.cpp:176-204, 295-322, 442-481 for
  * one CSR (gather CSR == scatter CSR, i.e. every case of an Unsigned operator and
@@ -181,7 +183,7 @@ int spn_ogs_extract(int N, int K, const int* ids, const void* q, void* gatherq, 
  * to the reference Serial kernels).  Built once at setup, like the reference operator.
  * ---------------------------------------------------------------------- */
 typedef struct spn_ogs_plan* spn_ogs_plan_t;
-int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h_rowStarts,
+int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h_rowStarts, const int* h_colIds,
                         const int* d_rowStarts, const int* d_colIds);
 int spn_ogs_plan_destroy(spn_ogs_plan_t plan);
 int spn_ogs_plan_info(spn_ogs_plan_t plan, int* Ntiles, int* Nirregular, size_t* plan_bytes);

@@ -18,18 +18,18 @@
 #define SPN_TILE_U_S SPN_TILE_U
 #define SPN_TILE_U_GS SPN_TILE_U
 #else
-#define SPN_TILE_U_G 3
+#define SPN_TILE_U_G 4
 #define SPN_TILE_U_S 8
-#define SPN_TILE_U_GS 6
+#define SPN_TILE_U_GS 8
 #endif
 #ifdef SPN_TILE_MINB
 #define SPN_TILE_MINB_G SPN_TILE_MINB
 #define SPN_TILE_MINB_S SPN_TILE_MINB
 #define SPN_TILE_MINB_GS SPN_TILE_MINB
 #else
-#define SPN_TILE_MINB_G 6
+#define SPN_TILE_MINB_G 4
 #define SPN_TILE_MINB_S 3
-#define SPN_TILE_MINB_GS 3
+#define SPN_TILE_MINB_GS 2
 #endif
 
 template <int MODE> struct TileGeom;
@@ -45,6 +45,8 @@ struct spn_ogs_plan {
   int nIrr;  // irregular rows
   long long nnz;
   unsigned* d_colP;  // packed ids, one 128-byte line per tile (owned)
+  unsigned* d_colPgs;  // gather+scatter tiles: rows re-ordered so that stores complete 32-byte sectors (owned, optional)
+  int NTgs;
   int* d_row0;       // first row of each tile (owned)
   int* d_irr;        // irregular rows (owned)
   int* d_rowOf;      // row of every column, -1 = none (owned); drives scatter
@@ -55,12 +57,65 @@ struct spn_ogs_plan {
 
 namespace {
 
-int g_variant = 0;  // experiment knob, see spn_debug_set
+// ---------------------------------------------------------------------------
+// Row order for the in-place gather+scatter.  The operation is free to visit rows in any
+// order (rows own disjoint columns), and which rows share a tile decides how many 32-byte
+// sectors each indexed store instruction completes: L2 ingests stores per sector, so a
+// sector written 8 bytes at a time by different tiles costs a transaction per visit
+// (measured: indexed 8-byte stores cost 1.7x their bytes with the first-appearance row
+// order, profiles/round1_notes.md).  Sweep the columns sector by sector; when a row is
+// emitted, immediately emit the rows of the sectors its OTHER columns live in, so both
+// ends of a shared node land in the same tile together with their sector neighbours.
+// Returns the packed id words (32 per tile).
+// ---------------------------------------------------------------------------
+void build_gs_tiles(int Nrows, int Ncols, const int* rs, const int* ci, std::vector<unsigned>& words) {
+  std::vector<int> rowOf((size_t)Ncols, -1);
+  for (int r = 0; r < Nrows; ++r)
+    for (int g = rs[r]; g < rs[r + 1]; ++g) rowOf[ci[g]] = r;
+  std::vector<char> emitted((size_t)Nrows, 0);
+  words.clear();
+  words.reserve((size_t)(rs[Nrows] - rs[0]) + (size_t)(rs[Nrows] - rs[0]) / 16 + 64);
+  int cur_n = 0;
+  auto flush = [&]() {
+    if (cur_n > 0) words.resize(words.size() + (size_t)(32 - cur_n), kEmptyLane);
+    cur_n = 0;
+  };
+  auto regular = [&](int r) { const int len = rs[r + 1] - rs[r]; return len >= 1 && len <= 32; };
+  auto append = [&](int r) {
+    const int len = rs[r + 1] - rs[r];
+    if (cur_n + len > 32) flush();
+    for (int g = rs[r]; g < rs[r + 1]; ++g) words.push_back((unsigned)ci[g] | (g == rs[r + 1] - 1 ? 0x80000000u : 0u));
+    cur_n += len;
+    emitted[r] = 1;
+  };
+  const int nsec = (Ncols + 3) / 4;
+  for (int s = 0; s < nsec; ++s) {
+    const int c1 = std::min(Ncols, 4 * s + 4);
+    for (int c = 4 * s; c < c1; ++c) {
+      const int r = rowOf[c];
+      if (r < 0 || emitted[r] || !regular(r)) continue;
+      append(r);
+      for (int g = rs[r]; g < rs[r + 1]; ++g) {  // complete the sectors of the row's other columns
+        const int s2 = ci[g] >> 2;
+        if (s2 == s) continue;
+        const int e2 = std::min(Ncols, 4 * s2 + 4);
+        for (int c2 = 4 * s2; c2 < e2; ++c2) {
+          const int r2 = rowOf[c2];
+          if (r2 >= 0 && !emitted[r2] && regular(r2)) append(r2);
+        }
+      }
+    }
+  }
+  flush();
+}
+
+int g_variant = 0;  // experiment knobs, see spn_debug_set
+int g_probe = 0;
 
 template <typename T, int OP, int MODE, int VAR>
-void launch_variant(int grid, cudaStream_t st, const spn_ogs_plan* p, const void* in, void* out) {
+void launch_variant(int grid, cudaStream_t st, const spn_ogs_plan* p, int NT, const unsigned* colP, const void* in, void* out) {
   ogs_tile_kernel<T, OP, MODE, TileGeom<MODE>::U, true, SPN_TILE_THREADS, TileGeom<MODE>::MINB, VAR>
-      <<<grid, SPN_TILE_THREADS, 0, st>>>(p->NT, 1, p->d_colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+      <<<grid, SPN_TILE_THREADS, 0, st>>>(NT, 1, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
 }
 
 template <typename T, int OP, int MODE>
@@ -68,11 +123,34 @@ int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaSt
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  if (p->NT > 0) {
+  // gather+scatter walks its own, sector-completing tile order when the plan has one
+  const bool gs_order = (MODE == TILE_GATHER_SCATTER) && p->d_colPgs != nullptr;
+  const unsigned* colP = gs_order ? p->d_colPgs : p->d_colP;
+  const int NT = gs_order ? p->NTgs : p->NT;
+  if (NT > 0) {
     constexpr int U = TileGeom<MODE>::U, TH = SPN_TILE_THREADS, MB = TileGeom<MODE>::MINB;
     static int resident_kone = 0, resident_k = 0;  // CTAs per SM (same for every sm_100 device)
-    const int warps_needed = (p->NT + U - 1) / U;
+    const int warps_needed = (NT + U - 1) / U;
     const int ctas_needed = (warps_needed + TH / 32 - 1) / (TH / 32);
+#ifndef SPN_TILE_NO_PF
+    if (K == 1 && MODE != TILE_SCATTER && !g_variant) {
+      constexpr int M2 = (MODE == TILE_SCATTER) ? TILE_GATHER : MODE;  // (scatter never reaches this kernel)
+      auto kern = ogs_tile_pf_kernel<T, OP, M2, U, TH, MB>;
+      static int resident_pf = 0;
+      if (!resident_pf) {
+        int per_sm = 0;
+        SPN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TH, 0));
+        resident_pf = per_sm > 0 ? per_sm : 1;
+      }
+      const int grid = std::min(ctas_needed, resident_pf * d->sms);
+      if (g_probe == 8)
+        ogs_tile_pf_kernel<T, OP, M2, U, TH, MB, 8><<<grid, TH, 0, st>>>(NT, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+      else if (g_probe == 16)
+        ogs_tile_pf_kernel<T, OP, M2, U, TH, MB, 16><<<grid, TH, 0, st>>>(NT, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+      else
+      kern<<<grid, TH, 0, st>>>(NT, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+    } else
+#endif
     if (K == 1) {
       auto kern = ogs_tile_kernel<T, OP, MODE, U, true, TH, MB>;
       if (!resident_kone) {
@@ -83,13 +161,13 @@ int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaSt
       const int grid = std::min(ctas_needed, resident_kone * d->sms);
       if (g_variant && sizeof(T) == 8 && OP == SPN_ADD && MODE == TILE_GATHER_SCATTER) {
         switch (g_variant) {
-          case 2: launch_variant<T, OP, MODE, 2>(grid, st, p, in, out); break;
-          case 4: launch_variant<T, OP, MODE, 4>(grid, st, p, in, out); break;
-          case 6: launch_variant<T, OP, MODE, 6>(grid, st, p, in, out); break;
+          case 2: launch_variant<T, OP, MODE, 2>(grid, st, p, NT, colP, in, out); break;
+          case 4: launch_variant<T, OP, MODE, 4>(grid, st, p, NT, colP, in, out); break;
+          case 6: launch_variant<T, OP, MODE, 6>(grid, st, p, NT, colP, in, out); break;
           default: return SPN_ERR_INVALID_ARGUMENT;
         }
       } else
-      kern<<<grid, TH, 0, st>>>(p->NT, K, p->d_colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+      kern<<<grid, TH, 0, st>>>(NT, K, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
     } else {
       auto kern = ogs_tile_kernel<T, OP, MODE, U, false, TH, MB>;
       if (!resident_k) {
@@ -98,7 +176,7 @@ int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaSt
         resident_k = per_sm > 0 ? per_sm : 1;
       }
       const int grid = std::min(ctas_needed, resident_k * d->sms);
-      kern<<<grid, TH, 0, st>>>(p->NT, K, p->d_colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+      kern<<<grid, TH, 0, st>>>(NT, K, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
     }
     SPN_LAUNCH_CHECK();
   }
@@ -136,8 +214,8 @@ int dispatch_type(const spn_ogs_plan* p, int K, const void* in, void* out, int t
 
 extern "C" {
 
-int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h_rowStarts, const int* d_rowStarts,
-                        const int* d_colIds) {
+int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h_rowStarts, const int* h_colIds,
+                        const int* d_rowStarts, const int* d_colIds) {
   if (!plan || Nrows < 0 || Ncols < 0 || (Nrows > 0 && (!h_rowStarts || !d_rowStarts || !d_colIds)))
     return SPN_ERR_INVALID_ARGUMENT;
   DeviceInfo* d;
@@ -153,6 +231,8 @@ int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h
   p->d_row0 = nullptr;
   p->d_irr = nullptr;
   p->d_rowOf = nullptr;
+  p->d_colPgs = nullptr;
+  p->NTgs = 0;
   p->Ncols = Ncols;
 
   // greedy packing of whole consecutive rows into <=32-nnz tiles
@@ -202,6 +282,14 @@ int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h
     SPN_CUDA_TRY(cudaMalloc(&p->d_irr, sizeof(int) * irr.size()));
     SPN_CUDA_TRY(cudaMemcpy(p->d_irr, irr.data(), sizeof(int) * irr.size(), cudaMemcpyHostToDevice));
   }
+  if (h_colIds && Ncols > 0 && p->NT > 0 && g_variant != 32) {
+    std::vector<unsigned> words;
+    build_gs_tiles(Nrows, Ncols, h_rowStarts, h_colIds, words);
+    p->NTgs = (int)(words.size() / 32);
+    words.resize(words.size() + (size_t)32 * kTilePad, kEmptyLane);
+    SPN_CUDA_TRY(cudaMalloc(&p->d_colPgs, sizeof(unsigned) * words.size()));
+    SPN_CUDA_TRY(cudaMemcpy(p->d_colPgs, words.data(), sizeof(unsigned) * words.size(), cudaMemcpyHostToDevice));
+  }
   if (Ncols > 0) {
     // inverse map for scatter: rowOf[c] = row holding column c, -1 if none
     SPN_CUDA_TRY(cudaMalloc(&p->d_rowOf, sizeof(int) * (size_t)Ncols));
@@ -226,6 +314,7 @@ int spn_ogs_plan_destroy(spn_ogs_plan_t plan) {
   if (plan->d_colP) cudaFree(plan->d_colP);
   if (plan->d_row0) cudaFree(plan->d_row0);
   if (plan->d_rowOf) cudaFree(plan->d_rowOf);
+  if (plan->d_colPgs) cudaFree(plan->d_colPgs);
   if (plan->d_irr) cudaFree(plan->d_irr);
   delete plan;
   return SPN_SUCCESS;
@@ -288,6 +377,7 @@ int spn_ogs_plan_scatter(spn_ogs_plan_t plan, int K, const void* gv, void* v, in
 
 int spn_debug_set(int key, int value) {
   if (key == 0) { g_variant = value; return SPN_SUCCESS; }
+  if (key == 1) { g_probe = value; return SPN_SUCCESS; }
   return SPN_ERR_INVALID_ARGUMENT;
 }
 

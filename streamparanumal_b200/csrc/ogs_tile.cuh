@@ -239,6 +239,104 @@ ogs_tile_kernel(int NT, int K, const unsigned* __restrict__ colP, const int* __r
 }
 
 // ---------------------------------------------------------------------------
+// K == 1 gather / gather+scatter with a three-deep register pipeline per warp:
+//   iteration i :  load ids of tiles i+2  |  indexed loads of tiles i+1  |  fold + store tiles i
+// so a warp never waits for the memory it has just asked for: the values it folds were
+// requested one whole iteration earlier.
+// ---------------------------------------------------------------------------
+template <typename T, int OP, int MODE, int U, int THREADS, int MINB, int VAR = 0>
+__global__ void __launch_bounds__(THREADS, MINB)
+ogs_tile_pf_kernel(int NT, const unsigned* __restrict__ colP, const int* __restrict__ row0, const T* in, T* out) {
+  static_assert(MODE == TILE_GATHER || MODE == TILE_GATHER_SCATTER, "scatter runs by columns");
+  static_assert(U <= kTilePad, "tile padding too small");
+  const int lane = threadIdx.x & 31;
+  const int warp = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 5);
+  const int nwarps = (int)((gridDim.x * (unsigned)THREADS) >> 5);
+  const unsigned le_mask = 0xffffffffu >> (31 - lane);
+  const int64_t step = (int64_t)nwarps * U;
+
+  int64_t base = (int64_t)warp * U;
+  if (base >= NT) return;
+
+  unsigned wc[U], w1[U];
+  int rc[U], r1[U];
+  T xc[U];
+  {
+    const int64_t t1 = (base + step < NT) ? base + step : base;  // clamped: harmless re-read
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      wc[u] = ld_ids(colP + 32 * (base + u) + lane);
+      w1[u] = ld_ids(colP + 32 * (t1 + u) + lane);
+      rc[u] = (MODE == TILE_GATHER) ? __ldg(row0 + base + u) : 0;
+      r1[u] = (MODE == TILE_GATHER) ? __ldg(row0 + t1 + u) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      xc[u] = (wc[u] != kEmptyLane) ? ld_once<T>(in + (wc[u] & 0x7fffffffu)) : OgsOp<T, OP>::init();
+  }
+
+  while (true) {
+    // ---- ids two iterations ahead, values one iteration ahead
+    unsigned w2[U];
+    int r2[U];
+    T x1[U];
+    {
+      const int64_t t2 = (base + 2 * step < NT) ? base + 2 * step : base;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        w2[u] = ld_ids(colP + 32 * (t2 + u) + lane);
+        r2[u] = (MODE == TILE_GATHER) ? __ldg(row0 + t2 + u) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        x1[u] = (w1[u] != kEmptyLane) ? ld_once<T>(in + (w1[u] & 0x7fffffffu)) : OgsOp<T, OP>::init();
+    }
+
+    // ---- row structure of the current tiles from the sign bits
+    unsigned last[U];
+    int pos[U], maxpos = 0;
+    T acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool valid = (wc[u] != kEmptyLane);
+      last[u] = __ballot_sync(0xffffffffu, valid && (wc[u] >> 31));
+      const unsigned heads = ((last[u] << 1) | 1u) & le_mask;
+      pos[u] = valid ? lane - (31 - __clz(heads)) : 0;
+      maxpos = max(maxpos, pos[u]);
+      acc[u] = OgsOp<T, OP>::init();
+      OgsOp<T, OP>::apply(acc[u], xc[u]);
+    }
+    // (VAR 8 / 16: timing probes that force 0 / 7 rounds — results are then wrong)
+    const int R = (VAR & 8) ? 0 : (VAR & 16) ? 7 : __reduce_max_sync(0xffffffffu, maxpos);
+    for (int t = 1; t <= R; ++t) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) fold_step<T, OP>(acc[u], shfl_up1(acc[u]), xc[u], pos[u], t);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool valid = (wc[u] != kEmptyLane);
+      if (MODE == TILE_GATHER) {
+        const unsigned heads = ((last[u] << 1) | 1u) & le_mask;
+        if (valid && (wc[u] >> 31)) out[rc[u] + __popc(heads) - 1] = acc[u];
+      } else {
+        const int lastlane = lane + __ffs(last[u] >> lane) - 1;
+        const T total = shfl_idx(acc[u], lastlane & 31);
+        if (valid) __stcs(out + (wc[u] & 0x7fffffffu), total);
+      }
+    }
+
+    base += step;
+    if (base >= NT) break;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      wc[u] = w1[u]; w1[u] = w2[u];
+      rc[u] = r1[u]; r1[u] = r2[u];
+      xc[u] = x1[u];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // scatter by columns.  Every column belongs to at most one row (the ogs invariant,
 // include/ogs/ogsOperator.hpp:41-43), so v[colIds[g]] = gv[row] for all g is the same
 // as v[c] = gv[rowOf[c]] for every column c that has a row: a pure streaming kernel

@@ -19,6 +19,18 @@
 #ifndef SPN_RED_CTAS_PER_SM
 #define SPN_RED_CTAS_PER_SM 4
 #endif
+// BS5 streams like axpby (read Ap, read+write r): the sweep in profiles/round1_notes.md has it
+// fastest as 128-bit accesses, 8 in flight per thread, 256-thread CTAs and a grid that is NOT
+// capped to the SM count (one CTA per 4096 entries, partials folded by the last CTA)
+#ifndef SPN_CG_BLOCK
+#define SPN_CG_BLOCK 256
+#endif
+#ifndef SPN_CG_UNROLL
+#define SPN_CG_UNROLL 8
+#endif
+#ifndef SPN_CG_MAXVEC
+#define SPN_CG_MAXVEC 2
+#endif
 
 using namespace spn;
 
@@ -98,12 +110,13 @@ int launch_cg(int64_t n, const double* Ap, double alpha, double* r, double* out,
   ReduceWs* ws;
   rc = resolve_workspace(d, workspace, &ws);
   if (rc) return rc;
-  const int vec = common_vec(Ap, r);
-  const int grid = red_grid(d, n, vec);
+  const int vec = std::min(common_vec(Ap, r), SPN_CG_MAXVEC);
+  int64_t g = (n / vec + (int64_t)SPN_CG_BLOCK * SPN_CG_UNROLL - 1) / ((int64_t)SPN_CG_BLOCK * SPN_CG_UNROLL);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(g, kMaxPartials));
   switch (vec) {
-    case 4: cg_update_kernel<4, SPN_RED_UNROLL, SPN_RED_BLOCK><<<grid, SPN_RED_BLOCK, 0, st>>>(n, Ap, alpha, r, ws, out, zero_tail); break;
-    case 2: cg_update_kernel<2, SPN_RED_UNROLL, SPN_RED_BLOCK><<<grid, SPN_RED_BLOCK, 0, st>>>(n, Ap, alpha, r, ws, out, zero_tail); break;
-    default: cg_update_kernel<1, SPN_RED_UNROLL, SPN_RED_BLOCK><<<grid, SPN_RED_BLOCK, 0, st>>>(n, Ap, alpha, r, ws, out, zero_tail); break;
+    case 4: cg_update_kernel<4, SPN_CG_UNROLL, SPN_CG_BLOCK><<<grid, SPN_CG_BLOCK, 0, st>>>(n, Ap, alpha, r, ws, out, zero_tail); break;
+    case 2: cg_update_kernel<2, SPN_CG_UNROLL, SPN_CG_BLOCK><<<grid, SPN_CG_BLOCK, 0, st>>>(n, Ap, alpha, r, ws, out, zero_tail); break;
+    default: cg_update_kernel<1, SPN_CG_UNROLL, SPN_CG_BLOCK><<<grid, SPN_CG_BLOCK, 0, st>>>(n, Ap, alpha, r, ws, out, zero_tail); break;
   }
   SPN_LAUNCH_CHECK();
   return SPN_SUCCESS;

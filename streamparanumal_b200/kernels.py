@@ -149,7 +149,7 @@ class OgsPlan:
     libs/ogs/ogsOperator.cpp:597-665).  rowStarts is a host int32 array; d_rowStarts /
     d_colIds are the device copies (kept alive by this object)."""
 
-    def __init__(self, rowStarts, d_rowStarts, d_colIds, Ncols):
+    def __init__(self, rowStarts, d_rowStarts, d_colIds, Ncols, colIds=None):
         import ctypes
         import numpy as np
         rs = np.ascontiguousarray(rowStarts, dtype=np.int32)
@@ -157,7 +157,9 @@ class OgsPlan:
         self._keep = (d_rowStarts, d_colIds)
         self._h = ctypes.c_void_p()
         self.Ncols = int(Ncols)
+        ci = None if colIds is None else np.ascontiguousarray(colIds, dtype=np.int32)
         check(_lib.kernel_lib().spn_ogs_plan_create(ctypes.byref(self._h), self.Nrows, self.Ncols, rs.ctypes.data,
+                                                    None if ci is None else ci.ctypes.data,
                                                     _dev(d_rowStarts, torch.int32), _dev(d_colIds, torch.int32)),
               "ogs plan create")
         nt, nirr, nbytes = ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()

@@ -184,7 +184,7 @@ def test_ogs_kernels_bit_exact(K, oracle, dtype, Kv, npb):
         bs = oracle.block_rows(rs, limit) if npb == 512 else util.greedy_blocks(rs, limit)
         nb = bs.size - 1
         d_bs, d_rs, d_ci = dev(bs), dev(rs), dev(ci)
-        plan = K.OgsPlan(rs, d_rs, d_ci, ids.size)
+        plan = K.OgsPlan(rs, d_rs, d_ci, ids.size, colIds=ci)
         v = _values(ids.size * Kv, dtype, 20 + m)
         for op in _ops_for(dtype):
             if op == 1 and not np.issubdtype(dtype, np.floating):
@@ -266,7 +266,7 @@ def test_ogs_high_multiplicity_and_masked_nodes(K, oracle):
     assert np.array_equal(dout.cpu().numpy(), oracle.ogs_scatter(rs, ci, dgv.cpu().numpy(), np.full(n, -1.0)))
     # warp-tile plan: the long rows (> 32) go through the irregular-row kernel
     d_rs, d_ci = dev(rs), dev(ci)
-    plan = K.OgsPlan(rs, d_rs, d_ci, ids.size)
+    plan = K.OgsPlan(rs, d_rs, d_ci, ids.size, colIds=ci)
     assert plan.Nirregular >= 2
     g2 = torch.zeros_like(dgv)
     plan.gather(1, dv, g2)

@@ -42,7 +42,7 @@ def main():
     b6 = 4 * (Ng + 1) + 4 * Nt + 8 * Nt + 8 * Ng
     b8 = 4 * (Ng + 1) + 4 * Nt + 16 * Nt
     t0 = time.time()
-    plan = K.OgsPlan(rs, d_rs, d_ci, Nt)
+    plan = K.OgsPlan(rs, d_rs, d_ci, Nt, colIds=None if os.environ.get("OGS_NO_GS_ORDER") else ci)
     print(f"plan: {plan.Ntiles} tiles ({Nt / max(plan.Ntiles, 1):.1f} nnz/tile), {plan.Nirregular} irregular rows, "
           f"{plan.plan_bytes / 1e6:.1f} MB, built in {time.time() - t0:.2f}s", flush=True)
     tg = timeit(lambda: plan.gather(1, v, gv))
@@ -61,6 +61,11 @@ def main():
             t2 = timeit(lambda: plan.gather_scatter_to(1, v, w), iters=50)
             print(f"probe variant {var}: in-place {t*1e3:.3f} ms {b8/t*1e-9:7.1f} GB/s | out-of-place {t2*1e3:.3f} ms", flush=True)
         _lib.kernel_lib().spn_debug_set(0, 0)
+        for probe in (8, 16, 0):
+            _lib.kernel_lib().spn_debug_set(1, probe)
+            t = timeit(lambda: plan.gather_scatter(1, v), iters=50)
+            tg2 = timeit(lambda: plan.gather(1, v, gv))
+            print(f"probe rounds {probe} (8: R=0, 16: R=7, 0: real): gs {t*1e3:.3f} ms {b8/t*1e-9:7.1f} GB/s | gather {tg2*1e3:.3f} ms {b6/tg2*1e-9:7.1f} GB/s", flush=True)
     for lim in limits:
         bs = util.greedy_blocks(rs, lim)
         nb = bs.size - 1
