@@ -1,16 +1,16 @@
 # Builds the sm_100a device backend (C ABI in include/spn_b200.h), the C++ host
 # layer and the BS executables.  nvcc cross-compiles without a GPU.
 NVCC      ?= /usr/local/cuda/bin/nvcc
-CXX       ?= g++
+CXX       := g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude $(SPN_TUNE)
 CSRC      := streamparanumal_b200/csrc
 LIBDIR    := streamparanumal_b200/lib
 
-KERNEL_SRCS := $(CSRC)/runtime.cu $(CSRC)/stream_abi.cu $(CSRC)/ogs_abi.cu $(CSRC)/ogs_plan.cu
+KERNEL_SRCS := $(CSRC)/runtime.cu $(CSRC)/stream_abi.cu $(CSRC)/ogs_abi.cu $(CSRC)/ogs_plan.cu $(CSRC)/ogs_halo.cu
 KERNEL_HDRS := $(CSRC)/common.cuh $(CSRC)/stream_kernels.cuh $(CSRC)/ogs_kernels.cuh $(CSRC)/ogs_pipe.cuh $(CSRC)/ogs_tile.cuh include/spn_b200.h
 
-all: $(LIBDIR)/libspn_b200.so $(LIBDIR)/libspn_b200_comm.so
+all: $(LIBDIR)/libspn_b200.so $(LIBDIR)/libspn_b200_comm.so $(LIBDIR)/libspn_host.so
 
 $(LIBDIR)/libspn_b200.so: $(KERNEL_SRCS) $(KERNEL_HDRS)
 	@mkdir -p $(LIBDIR)
@@ -19,6 +19,14 @@ $(LIBDIR)/libspn_b200.so: $(KERNEL_SRCS) $(KERNEL_HDRS)
 $(LIBDIR)/libspn_b200_comm.so: $(CSRC)/comm_nccl.cu include/spn_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/comm_nccl.cu -cudart static -lnccl
+
+# C++ host layer (mirror of the reference's ogs / platform / comm API) + its C binding
+HOST      := streamparanumal_b200/host
+HOST_SRCS := $(HOST)/comm.cpp $(HOST)/platform.cpp $(HOST)/ogs_setup.cpp $(HOST)/ogs_ops.cpp $(HOST)/mesh.cpp $(HOST)/capi.cpp
+HOST_HDRS := $(HOST)/comm.hpp $(HOST)/platform.hpp $(HOST)/ogs.hpp include/spn_b200.h include/spn_host.h
+CXXFLAGS  := -O2 -g -std=c++17 -fPIC -fopenmp -Wall -Iinclude -I$(HOST)
+$(LIBDIR)/libspn_host.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/libspn_b200.so $(LIBDIR)/libspn_b200_comm.so
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) -L$(LIBDIR) -lspn_b200 -lspn_b200_comm -Wl,-rpath,'$$ORIGIN'
 
 ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/stream_abi.cu 2>&1 | grep -E "Compiling|registers|spill"

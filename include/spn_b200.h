@@ -197,6 +197,27 @@ int spn_ogs_plan_gather_scatter_to(spn_ogs_plan_t plan, int K, const void* v, vo
 int spn_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------
+ * Halo side of the pairwise exchange.  The reference brackets its MPI exchange with four
+ * kernels — halo gather (libs/ogs/ogs.cpp:58), extract into per-neighbour order
+ * (libs/ogs/ogsPairwise.cpp:115), postmpi gather of own + received partials (:155) and halo
+ * scatter (libs/ogs/ogs.cpp:124).  These two entry points are the same arithmetic in two
+ * launches:
+ *   gather_pack:      ownBuf[k+row*K]  = OP_{g in halo row} v[k+colIds[g]*K]            row < Nrows
+ *                     sendBuf[k+s*K]   = the same fold for row sendIds[s]               s < Nsend
+ *   combine_scatter:  acc = identity OP own[k+row*K] (only if row < NrowsP)
+ *                               OP recvBuf[k+cmbIds[j]*K], j in [cmbStarts[row],cmbStarts[row+1]) in order
+ *                     sRowStarts != NULL: out[k+sColIds[g]*K] = acc for every g of the row (scatter to v)
+ *                     sRowStarts == NULL: out[k+row*K] = acc              (gathered layout, ogs.cpp:276)
+ * cmbIds lists the receive slots of a row in ascending source rank, which is the reference's
+ * summation order (own partial first, then remote partials by rank: ogsPairwise.cpp:214-232).
+ * ---------------------------------------------------------------------- */
+int spn_ogs_halo_gather_pack(int Nrows, int Nsend, int K, const int* rowStarts, const int* colIds, const int* sendIds,
+                             const void* v, void* ownBuf, void* sendBuf, int type, int op, spn_stream_t stream);
+int spn_ogs_halo_combine_scatter(int Nrows, int NrowsP, int K, const int* cmbStarts, const int* cmbIds,
+                                 const void* ownBuf, const void* recvBuf, const int* sRowStarts, const int* sColIds,
+                                 void* out, int type, int op, spn_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Device-buffer communication over NCCL — replaces comm_t::{Isend,Irecv,
  * Waitall} on device pointers (libs/ogs/ogsPairwise.cpp:135-152) and adds the
  * scalar allreduce the north-star asks for after norm/dot/rdotr.

@@ -76,6 +76,8 @@ KERNEL_SIGNATURES = {
     "spn_ogs_plan_gather_scatter": [_P, c_int, _P, c_int, c_int, _P],
     "spn_ogs_plan_gather_scatter_to": [_P, c_int, _P, _P, c_int, c_int, _P],
     "spn_debug_set": [c_int, c_int],
+    "spn_ogs_halo_gather_pack": [c_int, c_int, c_int, _IP, _IP, _IP, _P, _P, _P, c_int, c_int, _P],
+    "spn_ogs_halo_combine_scatter": [c_int, c_int, c_int, _IP, _IP, _P, _P, _IP, _IP, _P, c_int, c_int, _P],
 }
 
 COMM_SIGNATURES = {

@@ -1,0 +1,196 @@
+// C binding of the host layer (include/spn_host.h).
+#include <string>
+#include <cstdlib>
+#include <unistd.h>
+
+#include "ogs.hpp"
+#include "spn_host.h"
+
+using namespace spn;
+
+struct spn_host_comm { comm_t comm; };
+struct spn_host_platform { platform_t platform; };
+struct spn_host_ogs { ogs::ogs_t ogs; };
+
+namespace {
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return SPN_SUCCESS;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return SPN_ERR_HOST;
+  }
+}
+Comm::Op to_op(int op) { return op == 1 ? Comm::Max : op == 2 ? Comm::Min : Comm::Sum; }
+}  // namespace
+
+extern "C" {
+
+const char* spn_host_last_error(void) { return g_last_error.c_str(); }
+
+int spn_host_comm_create(spn_host_comm_t* comm, int rank, int size, const char* dir) {
+  if (!comm) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] {
+    if (dir) *comm = new spn_host_comm{comm_t(rank, size, dir)};
+    else {
+      const char* port = getenv("MASTER_PORT");
+      *comm = new spn_host_comm{comm_t(rank, size, std::string("/tmp/spn_rdv_") + std::to_string((long)getuid()) + "_" + (port ? port : "0"))};
+    }
+  });
+}
+int spn_host_comm_create_world(spn_host_comm_t* comm) {
+  if (!comm) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { *comm = new spn_host_comm{comm_t::World()}; });
+}
+int spn_host_comm_destroy(spn_host_comm_t comm) { delete comm; return SPN_SUCCESS; }
+int spn_host_comm_rank(spn_host_comm_t comm, int* rank) { if (!comm || !rank) return SPN_ERR_INVALID_ARGUMENT; *rank = comm->comm.rank(); return 0; }
+int spn_host_comm_size(spn_host_comm_t comm, int* size) { if (!comm || !size) return SPN_ERR_INVALID_ARGUMENT; *size = comm->comm.size(); return 0; }
+int spn_host_comm_barrier(spn_host_comm_t comm) { if (!comm) return SPN_ERR_INVALID_ARGUMENT; return guarded([&] { comm->comm.Barrier(); }); }
+int spn_host_comm_allreduce_i64(spn_host_comm_t comm, long long* buf, int n, int op) {
+  if (!comm || !buf) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { comm->comm.Allreduce(buf, n, to_op(op)); });
+}
+int spn_host_comm_allreduce_f64(spn_host_comm_t comm, double* buf, int n, int op) {
+  if (!comm || !buf) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { comm->comm.Allreduce(buf, n, to_op(op)); });
+}
+int spn_host_comm_allreduce_device_f64(spn_host_comm_t comm, double* d_buf, int n, spn_stream_t stream) {
+  if (!comm) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { comm->comm.AllreduceDevice(d_buf, n, stream); });
+}
+
+int spn_host_platform_create(spn_host_platform_t* platform, spn_host_comm_t comm, int device_id) {
+  if (!platform || !comm) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { *platform = new spn_host_platform{platform_t(comm->comm, device_id)}; });
+}
+int spn_host_platform_destroy(spn_host_platform_t platform) { delete platform; return SPN_SUCCESS; }
+int spn_host_platform_set_stream(spn_host_platform_t platform, spn_stream_t stream) {
+  if (!platform) return SPN_ERR_INVALID_ARGUMENT;
+  platform->platform.setStream(stream);
+  return SPN_SUCCESS;
+}
+int spn_host_platform_finish(spn_host_platform_t platform) {
+  if (!platform) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { platform->platform.finish(); });
+}
+
+int spn_host_box_hex_ids(int rank, int size, int nx, int ny, int nz, int p, long long* ids, long long* Nglobal) {
+  if (!ids || size < 1 || rank < 0 || rank >= size || nx < 1 || ny < 1 || nz < 1 || p < 1) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { BoxHexGlobalIds(rank, size, nx, ny, nz, p, ids, Nglobal); });
+}
+
+int spn_host_ogs_setup(spn_host_ogs_t* ogs, int N, long long* ids, spn_host_comm_t comm, int kind, int unique, int verbose,
+                       spn_host_platform_t platform) {
+  if (!ogs || !comm || N < 0 || (N > 0 && !ids)) return SPN_ERR_INVALID_ARGUMENT;
+  *ogs = nullptr;
+  spn_host_ogs* o = new spn_host_ogs();
+  const int rc = guarded([&] {
+    if (platform) o->ogs.Setup(N, ids, comm->comm, (ogs::Kind)kind, ogs::Auto, unique != 0, verbose != 0, platform->platform);
+    else o->ogs.SetupHost(N, ids, comm->comm, (ogs::Kind)kind, unique != 0, verbose != 0);
+  });
+  if (rc) { delete o; return rc; }
+  *ogs = o;
+  return SPN_SUCCESS;
+}
+int spn_host_ogs_free(spn_host_ogs_t ogs) { delete ogs; return SPN_SUCCESS; }
+
+int spn_host_ogs_info(spn_host_ogs_t h, long long* info) {
+  if (!h || !info) return SPN_ERR_INVALID_ARGUMENT;
+  const ogs::ogs_t& o = h->ogs;
+  for (int i = 0; i < 16; ++i) info[i] = 0;
+  info[0] = o.N; info[1] = o.Ngather; info[2] = o.NgatherGlobal; info[3] = o.NlocalT; info[4] = o.NlocalP;
+  info[5] = o.NhaloT; info[6] = o.NhaloP; info[7] = o.gather_defined ? 1 : 0;
+  if (o.gatherLocal) { info[8] = o.gatherLocal->nnzT; info[9] = o.gatherLocal->nnzN; }
+  if (o.gatherHalo) { info[10] = o.gatherHalo->nnzT; info[11] = o.gatherHalo->nnzN; }
+  if (o.gatherLocal && o.gatherLocal->planT) {
+    int nt = 0;
+    spn_ogs_plan_info(o.gatherLocal->planT, &nt, nullptr, nullptr);
+    info[12] = nt;
+  }
+  return SPN_SUCCESS;
+}
+int spn_host_ogs_exchange_info(spn_host_ogs_t h, int mode, long long* info) {
+  if (!h || !info || mode < 0 || mode > 2) return SPN_ERR_INVALID_ARGUMENT;
+  const ogs::ogsExchangeData_t& d = h->ogs.data[mode];
+  info[0] = d.Nsend; info[1] = d.Nrecv; info[2] = d.NrowsP; info[3] = d.Nrows;
+  info[4] = (long long)d.sendRanks.size(); info[5] = (long long)d.recvRanks.size(); info[6] = info[7] = 0;
+  return SPN_SUCCESS;
+}
+int spn_host_ogs_array(spn_host_ogs_t h, int which, int mode, const int** ptr, long long* len) {
+  if (!h || !ptr || !len || mode < 0 || mode > 2) return SPN_ERR_INVALID_ARGUMENT;
+  const ogs::ogs_t& o = h->ogs;
+  if (!o.gatherLocal || !o.gatherHalo) return SPN_ERR_INVALID_ARGUMENT;
+  const ogs::ogsExchangeData_t& d = o.data[mode];
+  const std::vector<int>* v = nullptr;
+  // an Unsigned operator aliases N to T (libs/ogs/ogsOperator.cpp:644-650)
+  auto nOrT = [](const ogs::ogsOperator_t& op, bool starts) -> const std::vector<int>* {
+    if (op.kind == ogs::Signed) return starts ? &op.rowStartsN : &op.colIdsN;
+    return starts ? &op.rowStartsT : &op.colIdsT;
+  };
+  switch (which) {
+    case 0: v = &o.gatherLocal->rowStartsT; break;
+    case 1: v = &o.gatherLocal->colIdsT; break;
+    case 2: v = nOrT(*o.gatherLocal, true); break;
+    case 3: v = nOrT(*o.gatherLocal, false); break;
+    case 4: v = &o.gatherHalo->rowStartsT; break;
+    case 5: v = &o.gatherHalo->colIdsT; break;
+    case 6: v = nOrT(*o.gatherHalo, true); break;
+    case 7: v = nOrT(*o.gatherHalo, false); break;
+    case 8: v = &d.sendIds; break;
+    case 9: v = &d.sendRanks; break;
+    case 10: v = &d.sendCounts; break;
+    case 11: v = &d.sendOffsets; break;
+    case 12: v = &d.recvRanks; break;
+    case 13: v = &d.recvCounts; break;
+    case 14: v = &d.recvOffsets; break;
+    case 15: v = &d.cmbStarts; break;
+    case 16: v = &d.cmbIds; break;
+    case 17: v = &d.recvRows; break;
+    default: return SPN_ERR_INVALID_ARGUMENT;
+  }
+  *ptr = v->data();
+  *len = (long long)v->size();
+  return SPN_SUCCESS;
+}
+int spn_host_ogs_halo_labels(spn_host_ogs_t h, const long long** ptr, long long* len) {
+  if (!h || !ptr || !len || !h->ogs.gatherHalo) return SPN_ERR_INVALID_ARGUMENT;
+  *ptr = h->ogs.gatherHalo->rowLabel.data();
+  *len = (long long)h->ogs.gatherHalo->rowLabel.size();
+  return SPN_SUCCESS;
+}
+
+int spn_host_ogs_gather_scatter(spn_host_ogs_t h, void* v, int k, int type, int op, int trans) {
+  if (!h) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] {
+    h->ogs.GatherScatterStart(v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans);
+    h->ogs.GatherScatterFinish(v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans);
+  });
+}
+int spn_host_ogs_gather_scatter_start(spn_host_ogs_t h, void* v, int k, int type, int op, int trans) {
+  if (!h) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { h->ogs.GatherScatterStart(v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans); });
+}
+int spn_host_ogs_gather_scatter_finish(spn_host_ogs_t h, void* v, int k, int type, int op, int trans) {
+  if (!h) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { h->ogs.GatherScatterFinish(v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans); });
+}
+int spn_host_ogs_gather(spn_host_ogs_t h, void* gv, const void* v, int k, int type, int op, int trans) {
+  if (!h) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] {
+    h->ogs.GatherStart(gv, v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans);
+    h->ogs.GatherFinish(gv, v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans);
+  });
+}
+int spn_host_ogs_scatter(spn_host_ogs_t h, void* v, const void* gv, int k, int type, int trans) {
+  if (!h) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] {
+    h->ogs.ScatterStart(v, gv, k, (ogs::Type)type, (ogs::Transpose)trans);
+    h->ogs.ScatterFinish(v, gv, k, (ogs::Type)type, (ogs::Transpose)trans);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+// spn::ogs — host layer of the gather/scatter library, mirroring the reference's public ogs API
+// (include/ogs.hpp:178-341: enums, ogs_t::Setup, Gather / Scatter / GatherScatter and their
+// Start/Finish halves on deviceMemory<T>) over the C ABI of include/spn_b200.h.
+//
+// Same contract as the reference:
+//   * ids[n]==0: node n does not participate; ids[n]<0: "flagged" copy (Signed kind); with
+//     unique=true Setup picks ONE positive copy per label and writes the signs back into ids
+//     (libs/ogs/ogsSetup.cpp:120-150,355-382).
+//   * rows (gathered numbering): labels whose copies all live on this rank are "local" rows, labels
+//     shared with other ranks are "halo" rows; inside each set rows are numbered by first appearance,
+//     rows with a positive copy first (ogsSetup.cpp:492-559); columns ascend inside a row (:561-579).
+//   * a gathered vector is laid out [NlocalT local rows | NhaloP owned halo rows]
+//     (libs/ogs/ogs.cpp:253,276,295,490), Ngather = NlocalP + NhaloP (ogsSetup.cpp:191).
+//   * GatherScatter(Sym): every sharer sends its CSR-ordered partial to every other sharer; each
+//     rank folds own partial first, then the remote partials in ascending source rank
+//     (libs/ogs/ogsPairwise.cpp:214-232).  NoTrans: only positive copies send.  Trans: partials go
+//     to the positive copy only (ogsPairwise.cpp:292-377).
+// What is different (B200-native, by design):
+//   * the exchange is NCCL send/recv on a dedicated stream ordered by events — no device.finish()
+//     host syncs (the reference has 2-3 per call: ogs.cpp:74,104,117) and no host staging;
+//   * halo gather+pack and combine+scatter are one launch each (csrc/ogs_halo.cu);
+//   * the interior operator runs on the warp-tile plan (csrc/ogs_tile.cuh) when gather CSR == scatter CSR;
+//   * only the Pairwise exchange exists (Method is accepted and ignored): on NVSwitch every peer is
+//     one hop away, which is the case Pairwise is optimal for;
+//   * the positive copy of a label is picked by a hash of the label instead of the reference's
+//     rank-seeded LCG (libs/primitives/random.cpp) — results of every operation are independent of
+//     that choice except which rank stores a shared row of a gathered vector.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "platform.hpp"
+
+namespace spn {
+namespace ogs {
+
+/* enums: numeric values equal the reference's (include/ogs.hpp:178-200) and spn_type / spn_op */
+typedef enum { Float, Double, Int32, Int64 } Type;
+typedef enum { Add, Mul, Max, Min } Op;
+typedef enum { Sym, NoTrans, Trans } Transpose;
+typedef enum { Auto, Pairwise, CrystalRouter, AllToAll } Method;
+typedef enum { Unsigned, Signed, Halo } Kind;
+
+constexpr Type Dfloat = Double;
+constexpr Type Dlong = Int32;
+constexpr Type Hlong = Int64;
+
+template <typename T> struct ogsType;
+template <> struct ogsType<float> { static constexpr Type get() { return Float; } };
+template <> struct ogsType<double> { static constexpr Type get() { return Double; } };
+template <> struct ogsType<int> { static constexpr Type get() { return Int32; } };
+template <> struct ogsType<long long int> { static constexpr Type get() { return Int64; } };
+size_t Sizeof(Type type);
+
+// CSR gather operator with its "T" (all copies) and "N" (positive copies only) variants
+// (include/ogs/ogsOperator.hpp:44-138).  Host arrays are always built; upload() makes the device copies.
+class ogsOperator_t {
+ public:
+  Kind kind = Unsigned;
+  dlong Ncols = 0, NrowsN = 0, NrowsT = 0, nnzN = 0, nnzT = 0;
+  std::vector<dlong> rowStartsT, colIdsT;  // NrowsT+1, nnzT
+  std::vector<dlong> rowStartsN, colIdsN;  // NrowsT+1 (rows >= NrowsN are empty), nnzN
+  std::vector<hlong> rowLabel;             // |label| of every row
+
+  // device side
+  deviceMemory<dlong> o_rowStartsT, o_colIdsT, o_rowStartsN, o_colIdsN, o_blockRowStartsT, o_blockRowStartsN;
+  dlong NrowBlocksT = 0, NrowBlocksN = 0;  // launch partitions: T rows over rowStartsT, rows [0,NrowsN) over rowStartsN
+  spn_ogs_plan_t planT = nullptr, planN = nullptr;  // warp-tile plans (interior operator only)
+
+  ~ogsOperator_t();
+  void upload(platform_t& platform, bool tile_plans);
+
+  // device operations, semantics of libs/ogs/ogsOperator.cpp:176-204, 295-322, 442-481
+  void Gather(void* o_gv, const void* o_v, int k, Type type, Op op, Transpose trans, spn_stream_t stream);
+  void Scatter(void* o_v, const void* o_gv, int k, Type type, Transpose trans, spn_stream_t stream);
+  void GatherScatter(void* o_v, int k, Type type, Op op, Transpose trans, spn_stream_t stream);
+};
+
+// one exchange mode of the pairwise plan (reference: ogsPairwise_t::data_t, include/ogs/ogsExchange.hpp:168-195)
+struct ogsExchangeData_t {
+  dlong Nsend = 0, Nrecv = 0;
+  dlong NrowsP = 0;  // rows whose own partial takes part in the fold
+  dlong Nrows = 0;   // rows produced by the fold
+  std::vector<dlong> sendIds;                            // halo row of every send slot, (dest rank, label) order
+  std::vector<dlong> recvRows;                           // halo row of every receive slot, (source rank, label) order
+  std::vector<int> sendRanks, recvRanks;                 // neighbours, ascending
+  std::vector<dlong> sendCounts, sendOffsets, recvCounts, recvOffsets;  // per neighbour, in slots
+  std::vector<dlong> cmbStarts, cmbIds;                  // Nrows+1 / Nrecv: receive slots of each row, ascending source rank
+  deviceMemory<dlong> o_sendIds, o_cmbStarts, o_cmbIds;
+};
+
+class ogs_t {
+ public:
+  ogs_t() = default;
+  ~ogs_t() { Free(); }
+  ogs_t(const ogs_t&) = delete;
+  ogs_t& operator=(const ogs_t&) = delete;
+
+  platform_t platform;
+  comm_t comm;
+
+  dlong N = 0;
+  dlong Ngather = 0;        // owned gathered rows: NlocalP + NhaloP
+  hlong NgatherGlobal = 0;  // summed over ranks
+  dlong NlocalT = 0, NlocalP = 0, NhaloT = 0, NhaloP = 0;
+  Kind kind = Unsigned;
+  bool unique = false;
+  bool gather_defined = false;
+  bool on_device = false;
+
+  std::shared_ptr<ogsOperator_t> gatherLocal, gatherHalo;
+  ogsExchangeData_t data[3];  // indexed by Transpose
+
+  // Setup on a platform (device arrays, NCCL communicator when comm.size()>1).  ids is updated in
+  // place when unique (reference: ogs_t::Setup, libs/ogs/ogs... ogsSetup.cpp:87-290).
+  void Setup(const dlong N, hlong* ids, comm_t comm, const Kind kind, const Method method, const bool unique,
+             const bool verbose, platform_t& platform);
+  // host-only plan (no CUDA calls): what the CPU tests of the partition/exchange logic use
+  void SetupHost(const dlong N, hlong* ids, comm_t comm, const Kind kind, const bool unique, const bool verbose);
+  void Free();
+
+  // ---- device operations: raw-pointer core (type-erased), used by the templates and the C API ----
+  void GatherScatterStart(void* o_v, int k, Type type, Op op, Transpose trans);
+  void GatherScatterFinish(void* o_v, int k, Type type, Op op, Transpose trans);
+  void GatherStart(void* o_gv, const void* o_v, int k, Type type, Op op, Transpose trans);
+  void GatherFinish(void* o_gv, const void* o_v, int k, Type type, Op op, Transpose trans);
+  void ScatterStart(void* o_v, const void* o_gv, int k, Type type, Transpose trans);
+  void ScatterFinish(void* o_v, const void* o_gv, int k, Type type, Transpose trans);
+
+  // ---- the reference's signatures (include/ogs.hpp:251-341) ----
+  template <typename T> void GatherScatter(deviceMemory<T> o_v, const int k, const Op op, const Transpose trans) {
+    GatherScatterStart(o_v, k, op, trans);
+    GatherScatterFinish(o_v, k, op, trans);
+  }
+  template <typename T> void GatherScatterStart(deviceMemory<T> o_v, const int k, const Op op, const Transpose trans) {
+    GatherScatterStart(o_v.ptr(), k, ogsType<T>::get(), op, trans);
+  }
+  template <typename T> void GatherScatterFinish(deviceMemory<T> o_v, const int k, const Op op, const Transpose trans) {
+    GatherScatterFinish(o_v.ptr(), k, ogsType<T>::get(), op, trans);
+  }
+  template <typename T> void Gather(deviceMemory<T> o_gv, deviceMemory<T> o_v, const int k, const Op op, const Transpose trans) {
+    GatherStart(o_gv, o_v, k, op, trans);
+    GatherFinish(o_gv, o_v, k, op, trans);
+  }
+  template <typename T> void GatherStart(deviceMemory<T> o_gv, deviceMemory<T> o_v, const int k, const Op op, const Transpose trans) {
+    GatherStart(o_gv.ptr(), o_v.ptr(), k, ogsType<T>::get(), op, trans);
+  }
+  template <typename T> void GatherFinish(deviceMemory<T> o_gv, deviceMemory<T> o_v, const int k, const Op op, const Transpose trans) {
+    GatherFinish(o_gv.ptr(), o_v.ptr(), k, ogsType<T>::get(), op, trans);
+  }
+  template <typename T> void Scatter(deviceMemory<T> o_v, deviceMemory<T> o_gv, const int k, const Transpose trans) {
+    ScatterStart(o_v, o_gv, k, trans);
+    ScatterFinish(o_v, o_gv, k, trans);
+  }
+  template <typename T> void ScatterStart(deviceMemory<T> o_v, deviceMemory<T> o_gv, const int k, const Transpose trans) {
+    ScatterStart(o_v.ptr(), o_gv.ptr(), k, ogsType<T>::get(), trans);
+  }
+  template <typename T> void ScatterFinish(deviceMemory<T> o_v, deviceMemory<T> o_gv, const int k, const Transpose trans) {
+    ScatterFinish(o_v.ptr(), o_gv.ptr(), k, ogsType<T>::get(), trans);
+  }
+
+ private:
+  void SetupPlan(const dlong N, hlong* ids, comm_t comm, const Kind kind, const bool unique, const bool verbose);
+  void AssertGatherDefined() const;
+  void AllocBuffer(size_t Nbytes);  // reference: ogsPairwise_t::AllocBuffer, libs/ogs/ogsPairwise.cpp:389-402
+  void StartExchange(const ogsExchangeData_t& d, int k, Type type);   // pack done on the current stream -> NCCL on commStream
+  void FinishExchange();                                              // current stream waits for the receive
+
+  deviceMemory<char> o_ownBuf, o_sendBuf, o_recvBuf;
+  spn_stream_t commStream = nullptr;
+  spn_event_t packedEvent = nullptr, recvEvent = nullptr;
+  bool exchange_in_flight = false;
+};
+
+}  // namespace ogs
+
+// Box mesh of degree-p hex elements, nx*ny*nz elements per rank on the Factor3(size) process grid
+// (reference: libs/mesh/meshSetupBoxHex3D.cpp:31-131, libs/core/rankDecomp.cpp:55-91,166-213).
+// ids[e*Np+n] is the label of node n=i+j*Nq+k*Nq^2 of local element e=ex+ey*nx+ez*nx*ny: one more than
+// the node's index in the global (NX*p+1)(NY*p+1)(NZ*p+1) lattice, so coincident nodes — on this rank
+// or across ranks — share a label, which is what mesh_t::ConnectNodes converges to
+// (libs/mesh/meshConnectNodes.cpp:44-81) up to the label values themselves.
+void Factor3(const int n, int& nx, int& ny, int& nz);
+void RankDecomp3(int size_x, int size_y, int size_z, int& rank_x, int& rank_y, int& rank_z, const int rank);
+void BoxHexGlobalIds(int rank, int size, int nx, int ny, int nz, int p, hlong* ids, hlong* NgatherGlobalExpected);
+
+}  // namespace spn

@@ -1,0 +1,256 @@
+// Device operations of spn::ogs — orchestration of libs/ogs/ogs.cpp:40-125 (GatherScatter),
+// :206-301 (Gather), :395-492 (Scatter) and the operator dispatch of libs/ogs/ogsOperator.cpp:
+// 176-204, 295-322, 442-481, re-expressed on CUDA streams and events:
+//
+//   Start  (current stream)  halo gather + pack ............ spn_ogs_halo_gather_pack
+//          (comm stream)     waits for the pack, then ONE ncclGroup of send/recv (spn_comm_exchange)
+//   Finish (current stream)  interior operator ............. tile plan / CSR kernels, overlaps the exchange
+//                            waits for the receive, then
+//                            fold own + received, write copies  spn_ogs_halo_combine_scatter
+//
+// The reference needs device.finish() host syncs at ogs.cpp:74,104,117 and ogsPairwise.cpp:118-121;
+// here the host never waits.
+#include <algorithm>
+
+#include "ogs.hpp"
+
+namespace spn {
+namespace ogs {
+
+// ---------------------------------------------------------------------------------------------
+// ogsOperator_t
+// ---------------------------------------------------------------------------------------------
+ogsOperator_t::~ogsOperator_t() {
+  if (planT) spn_ogs_plan_destroy(planT);
+  if (planN && planN != planT) spn_ogs_plan_destroy(planN);
+}
+
+void ogsOperator_t::upload(platform_t& platform, bool tile_plans) {
+  if (NrowsT == 0) return;
+  o_rowStartsT = platform.malloc<dlong>(rowStartsT);
+  o_colIdsT = platform.malloc<dlong>(colIdsT);
+  if (kind == Signed) {
+    o_rowStartsN = platform.malloc<dlong>(rowStartsN);
+    if (nnzN) o_colIdsN = platform.malloc<dlong>(colIdsN);
+  } else {
+    o_rowStartsN = o_rowStartsT;
+    o_colIdsN = o_colIdsT;
+  }
+  // launch partitions of the CSR kernels: whole rows, <= spn_ogs_nodes_per_block() non-zeros per block
+  // (the role of blockRows(), libs/ogs/ogsOperator.cpp:522-594; a longer single row gets its own block)
+  auto partition = [&](const std::vector<dlong>& rs, dlong nrows, dlong& nblocks) {
+    const dlong limit = spn_ogs_nodes_per_block();
+    std::vector<dlong> blocks(1, 0);
+    dlong r = 0;
+    while (r < nrows) {
+      const dlong cap = rs[r] + limit;
+      dlong e = (dlong)(std::upper_bound(rs.begin() + r, rs.begin() + nrows + 1, cap) - rs.begin()) - 1;
+      e = std::min(std::max(e, r + 1), nrows);
+      blocks.push_back(e);
+      r = e;
+    }
+    nblocks = (dlong)blocks.size() - 1;
+    return platform.malloc<dlong>(blocks);
+  };
+  o_blockRowStartsT = partition(rowStartsT, NrowsT, NrowBlocksT);
+  if (kind == Signed) {
+    if (NrowsN) o_blockRowStartsN = partition(rowStartsN, NrowsN, NrowBlocksN);
+  } else {
+    o_blockRowStartsN = o_blockRowStartsT;
+    NrowBlocksN = NrowBlocksT;
+  }
+  if (tile_plans) {
+    SPN_CHECK(spn_ogs_plan_create(&planT, NrowsT, Ncols, rowStartsT.data(), colIdsT.data(), o_rowStartsT.ptr(),
+                                  o_colIdsT.ptr()));
+    if (kind == Signed && nnzN != nnzT) {
+      if (nnzN)
+        SPN_CHECK(spn_ogs_plan_create(&planN, NrowsN, Ncols, rowStartsN.data(), colIdsN.data(), o_rowStartsN.ptr(),
+                                      o_colIdsN.ptr()));
+    } else {
+      planN = planT;  // every copy is positive: the N operator is the T operator
+    }
+  }
+}
+
+void ogsOperator_t::Gather(void* o_gv, const void* o_v, int k, Type type, Op op, Transpose trans, spn_stream_t stream) {
+  if (NrowsT == 0) return;
+  const bool useN = (trans == NoTrans);  // libs/ogs/ogsOperator.cpp:185-203
+  if (useN && nnzN == 0) return;
+  spn_ogs_plan_t plan = useN ? planN : planT;
+  if (plan) {
+    SPN_CHECK(spn_ogs_plan_gather(plan, k, o_v, o_gv, type, op, stream));
+    return;
+  }
+  if (useN)  // rows [0, NrowsN) only, as the reference's NrowBlocksN launch
+    SPN_CHECK(spn_ogs_gather(NrowBlocksN, k, o_blockRowStartsN.ptr(), o_rowStartsN.ptr(), o_colIdsN.ptr(), o_v, o_gv, type, op, stream));
+  else
+    SPN_CHECK(spn_ogs_gather(NrowBlocksT, k, o_blockRowStartsT.ptr(), o_rowStartsT.ptr(), o_colIdsT.ptr(), o_v, o_gv, type, op, stream));
+}
+
+void ogsOperator_t::Scatter(void* o_v, const void* o_gv, int k, Type type, Transpose trans, spn_stream_t stream) {
+  if (NrowsT == 0) return;
+  const bool useN = (trans == Trans);  // libs/ogs/ogsOperator.cpp:303-321
+  if (useN && nnzN == 0) return;
+  spn_ogs_plan_t plan = useN ? planN : planT;
+  if (plan) {
+    SPN_CHECK(spn_ogs_plan_scatter(plan, k, o_gv, o_v, type, stream));
+    return;
+  }
+  if (useN)
+    SPN_CHECK(spn_ogs_scatter(NrowBlocksN, k, o_blockRowStartsN.ptr(), o_rowStartsN.ptr(), o_colIdsN.ptr(), o_gv, o_v, type, stream));
+  else
+    SPN_CHECK(spn_ogs_scatter(NrowBlocksT, k, o_blockRowStartsT.ptr(), o_rowStartsT.ptr(), o_colIdsT.ptr(), o_gv, o_v, type, stream));
+}
+
+void ogsOperator_t::GatherScatter(void* o_v, int k, Type type, Op op, Transpose trans, spn_stream_t stream) {
+  if (NrowsT == 0) return;
+  // gather / scatter CSR pairs of libs/ogs/ogsOperator.cpp:450-480 (Trans: T then N; Sym: T, T; NoTrans: N then T)
+  const bool same = (trans == Sym) || kind != Signed || nnzN == nnzT;
+  if (same) {
+    if (planT) SPN_CHECK(spn_ogs_plan_gather_scatter(planT, k, o_v, type, op, stream));
+    else
+      SPN_CHECK(spn_ogs_gather_scatter(NrowBlocksT, k, o_blockRowStartsT.ptr(), o_rowStartsT.ptr(), o_colIdsT.ptr(),
+                                       o_rowStartsT.ptr(), o_colIdsT.ptr(), o_v, type, op, stream));
+    return;
+  }
+  const dlong* gRS = (trans == Trans) ? o_rowStartsT.ptr() : o_rowStartsN.ptr();
+  const dlong* gCI = (trans == Trans) ? o_colIdsT.ptr() : o_colIdsN.ptr();
+  const dlong* sRS = (trans == Trans) ? o_rowStartsN.ptr() : o_rowStartsT.ptr();
+  const dlong* sCI = (trans == Trans) ? o_colIdsN.ptr() : o_colIdsT.ptr();
+  SPN_CHECK(spn_ogs_gather_scatter(NrowBlocksT, k, o_blockRowStartsT.ptr(), gRS, gCI, sRS, sCI, o_v, type, op, stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// ogs_t: buffers and the exchange
+// ---------------------------------------------------------------------------------------------
+void ogs_t::AllocBuffer(size_t Nbytes) {
+  const ogsExchangeData_t& d = data[Sym];  // the Sym plan bounds every mode (ogsPairwise.cpp:389-402)
+  if (o_ownBuf.size() < (size_t)NhaloT * Nbytes) o_ownBuf = platform.malloc<char>((size_t)NhaloT * Nbytes);
+  if (o_sendBuf.size() < (size_t)d.Nsend * Nbytes) o_sendBuf = platform.malloc<char>((size_t)d.Nsend * Nbytes);
+  if (o_recvBuf.size() < (size_t)d.Nrecv * Nbytes) o_recvBuf = platform.malloc<char>((size_t)d.Nrecv * Nbytes);
+}
+
+void ogs_t::StartExchange(const ogsExchangeData_t& d, int k, Type type) {
+  if (comm.size() == 1) return;
+  const size_t Nbytes = Sizeof(type) * (size_t)k;
+  spn_stream_t cur = platform.getStream();
+  SPN_CHECK(spn_event_record(packedEvent, cur));
+  SPN_CHECK(spn_stream_wait_event(commStream, packedEvent));
+  const int nr = (int)d.recvRanks.size(), ns = (int)d.sendRanks.size();
+  std::vector<size_t> ro(nr), rb(nr), so(ns), sb(ns);
+  for (int i = 0; i < nr; ++i) { ro[i] = (size_t)d.recvOffsets[i] * Nbytes; rb[i] = (size_t)d.recvCounts[i] * Nbytes; }
+  for (int i = 0; i < ns; ++i) { so[i] = (size_t)d.sendOffsets[i] * Nbytes; sb[i] = (size_t)d.sendCounts[i] * Nbytes; }
+  SPN_CHECK(spn_comm_exchange(comm.device(), nr, d.recvRanks.data(), ro.data(), rb.data(), o_recvBuf.ptr(), ns,
+                              d.sendRanks.data(), so.data(), sb.data(), o_sendBuf.ptr(), commStream));
+  SPN_CHECK(spn_event_record(recvEvent, commStream));
+  exchange_in_flight = true;
+}
+
+void ogs_t::FinishExchange() {
+  if (!exchange_in_flight) return;
+  SPN_CHECK(spn_stream_wait_event(platform.getStream(), recvEvent));
+  exchange_in_flight = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GatherScatter (libs/ogs/ogs.cpp:40-125)
+// ---------------------------------------------------------------------------------------------
+void ogs_t::GatherScatterStart(void* o_v, int k, Type type, Op op, Transpose trans) {
+  SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
+  if (NhaloT == 0 && comm.size() == 1) return;
+  AllocBuffer((size_t)k * Sizeof(type));
+  const ogsExchangeData_t& d = data[trans];
+  // halo partials: gather over the T copies unless NoTrans (positive copies only), straight into send order
+  const bool useN = (trans == NoTrans);
+  SPN_CHECK(spn_ogs_halo_gather_pack(NhaloT, d.Nsend, k, useN ? gatherHalo->o_rowStartsN.ptr() : gatherHalo->o_rowStartsT.ptr(),
+                                     useN ? gatherHalo->o_colIdsN.ptr() : gatherHalo->o_colIdsT.ptr(), d.o_sendIds.ptr(), o_v,
+                                     o_ownBuf.ptr(), o_sendBuf.ptr(), type, op, platform.getStream()));
+  StartExchange(d, k, type);
+}
+
+void ogs_t::GatherScatterFinish(void* o_v, int k, Type type, Op op, Transpose trans) {
+  SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
+  spn_stream_t cur = platform.getStream();
+  gatherLocal->GatherScatter(o_v, k, type, op, trans, cur);  // interior rows, overlaps the exchange
+  if (NhaloT == 0 && comm.size() == 1) return;
+  FinishExchange();
+  const ogsExchangeData_t& d = data[trans];
+  // scatter side: every copy, except Trans which writes positive copies only (ogsOperator.cpp:303-321)
+  const bool sN = (trans == Trans);
+  SPN_CHECK(spn_ogs_halo_combine_scatter(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), o_ownBuf.ptr(),
+                                         o_recvBuf.ptr(), sN ? gatherHalo->o_rowStartsN.ptr() : gatherHalo->o_rowStartsT.ptr(),
+                                         sN ? gatherHalo->o_colIdsN.ptr() : gatherHalo->o_colIdsT.ptr(), o_v, type, op, cur));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gather (libs/ogs/ogs.cpp:206-301): o_gv = [NlocalT local rows | NhaloP owned halo rows]
+// ---------------------------------------------------------------------------------------------
+void ogs_t::GatherStart(void* o_gv, const void* o_v, int k, Type type, Op op, Transpose trans) {
+  SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
+  AssertGatherDefined();
+  if (NhaloT == 0) return;
+  const size_t Nbytes = (size_t)k * Sizeof(type);
+  if (trans == Trans) {  // partials travel to the positive copy
+    AllocBuffer(Nbytes);
+    const ogsExchangeData_t& d = data[Trans];
+    SPN_CHECK(spn_ogs_halo_gather_pack(NhaloT, d.Nsend, k, gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(),
+                                       d.o_sendIds.ptr(), o_v, o_ownBuf.ptr(), o_sendBuf.ptr(), type, op, platform.getStream()));
+    StartExchange(d, k, type);
+  } else {  // no communication: gather the halo rows in place behind the local rows
+    gatherHalo->Gather(static_cast<char*>(o_gv) + Nbytes * (size_t)NlocalT, o_v, k, type, op, trans, platform.getStream());
+  }
+}
+
+void ogs_t::GatherFinish(void* o_gv, const void* o_v, int k, Type type, Op op, Transpose trans) {
+  SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
+  AssertGatherDefined();
+  spn_stream_t cur = platform.getStream();
+  gatherLocal->Gather(o_gv, o_v, k, type, op, trans, cur);
+  if (trans == Trans && NhaloT > 0) {
+    FinishExchange();
+    const ogsExchangeData_t& d = data[Trans];
+    const size_t Nbytes = (size_t)k * Sizeof(type);
+    // fold straight into the tail of o_gv (the reference folds into o_recvBuf and copies: ogs.cpp:270-277)
+    SPN_CHECK(spn_ogs_halo_combine_scatter(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), o_ownBuf.ptr(),
+                                           o_recvBuf.ptr(), nullptr, nullptr,
+                                           static_cast<char*>(o_gv) + Nbytes * (size_t)NlocalT, type, op, cur));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scatter (libs/ogs/ogs.cpp:395-492)
+// ---------------------------------------------------------------------------------------------
+void ogs_t::ScatterStart(void* /*o_v*/, const void* o_gv, int k, Type type, Transpose trans) {
+  SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
+  AssertGatherDefined();
+  if (trans != NoTrans || NhaloT == 0) return;
+  const size_t Nbytes = (size_t)k * Sizeof(type);
+  AllocBuffer(Nbytes);
+  const ogsExchangeData_t& d = data[NoTrans];
+  // owners pack their rows of o_gv straight into send order (the reference copies, then extracts: ogs.cpp:423-431)
+  SPN_CHECK(spn_ogs_extract(d.Nsend, k, d.o_sendIds.ptr(), static_cast<const char*>(o_gv) + Nbytes * (size_t)NlocalT,
+                            o_sendBuf.ptr(), type, platform.getStream()));
+  StartExchange(d, k, type);
+}
+
+void ogs_t::ScatterFinish(void* o_v, const void* o_gv, int k, Type type, Transpose trans) {
+  SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
+  AssertGatherDefined();
+  spn_stream_t cur = platform.getStream();
+  gatherLocal->Scatter(o_v, o_gv, k, type, trans, cur);
+  if (NhaloT == 0) return;
+  const size_t Nbytes = (size_t)k * Sizeof(type);
+  const char* gvHalo = static_cast<const char*>(o_gv) + Nbytes * (size_t)NlocalT;
+  if (trans == NoTrans) {
+    FinishExchange();
+    const ogsExchangeData_t& d = data[NoTrans];
+    // rows < NhaloP take their own value from o_gv, the others the owner's (identity (+) x, as postmpi.Gather does)
+    SPN_CHECK(spn_ogs_halo_combine_scatter(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), gvHalo, o_recvBuf.ptr(),
+                                           gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(), o_v, type, Add, cur));
+  } else {
+    gatherHalo->Scatter(o_v, gvHalo, k, type, trans, cur);
+  }
+}
+
+}  // namespace ogs
+}  // namespace spn

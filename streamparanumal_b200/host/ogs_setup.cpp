@@ -1,0 +1,444 @@
+// ogs_t::Setup — builds the gather operators and the pairwise exchange plan from the node labels.
+// Contract of the reference's ogsBase_t::Setup (libs/ogs/ogsSetup.cpp:87-290) and
+// ogsPairwise_t (libs/ogs/ogsPairwise.cpp:176-387); the algorithm is our own:
+//   1. every non-zero label is routed to a directory rank (|label| % size) in ONE alltoallv; the
+//      directory groups copies by label, decides shared / local, picks the positive copy when
+//      `unique`, and answers each copy with (shared flag, signed label) plus, per (label, rank) of
+//      a shared label, the list of ranks holding it and whether each holds a positive copy;
+//   2. rows are numbered locally (one parallel sort + linear passes);
+//   3. the per-neighbour send/receive lists are ordered by LABEL on both sides, so sender and
+//      receiver agree on the message layout without exchanging row indices (the reference ships
+//      remote row ids through four more alltoallv rounds: ogsSetup.cpp:617-813).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <parallel/algorithm>
+
+#include "ogs.hpp"
+
+namespace spn {
+namespace ogs {
+
+size_t Sizeof(Type type) {
+  switch (type) {
+    case Float: return 4;
+    case Double: return 8;
+    case Int32: return 4;
+    case Int64: return 8;
+  }
+  return 0;
+}
+
+namespace {
+
+inline hlong habs(hlong x) { return x < 0 ? -x : x; }
+
+// splitmix64 finaliser: picks the positive copy of a label deterministically
+inline unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+struct Key {
+  hlong label;  // |label|
+  dlong idx;    // position in the entry list
+};
+inline bool key_less(const Key& a, const Key& b) { return a.label < b.label || (a.label == b.label && a.idx < b.idx); }
+
+// Number the label groups of one entry set and build both CSR variants.
+// entries: signed labels `ids` at columns `cols` (cols strictly ascending).
+std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const std::vector<hlong>& ids,
+                                              const std::vector<dlong>& cols) {
+  auto op = std::make_shared<ogsOperator_t>();
+  op->kind = (kind == Unsigned) ? Unsigned : Signed;
+  op->Ncols = Ncols;
+  const dlong n = (dlong)ids.size();
+  op->nnzT = n;
+
+  std::vector<Key> keys((size_t)n);
+#pragma omp parallel for
+  for (dlong i = 0; i < n; ++i) keys[i] = Key{habs(ids[i]), i};
+  __gnu_parallel::sort(keys.begin(), keys.end(), key_less);
+
+  // group heads in sorted order
+  std::vector<dlong> groupOfSorted((size_t)n);
+  dlong NT = 0;
+  for (dlong i = 0; i < n; ++i) {
+    if (i == 0 || keys[i].label != keys[i - 1].label) ++NT;
+    groupOfSorted[i] = NT - 1;
+  }
+  std::vector<dlong> groupFirst((size_t)NT);  // entry index of the first appearance of each group
+  std::vector<char> groupPos((size_t)NT, 0);  // has a positive copy on this rank
+  for (dlong i = 0; i < n; ++i) {
+    const dlong g = groupOfSorted[i];
+    if (i == 0 || groupOfSorted[i - 1] != g) groupFirst[g] = keys[i].idx;  // smallest idx: sorted by (label, idx)
+    if (ids[keys[i].idx] > 0) groupPos[g] = 1;
+  }
+  // first-appearance order, positive groups first (libs/ogs/ogsSetup.cpp:492-559)
+  std::vector<dlong> headGroup((size_t)n, -1);
+  for (dlong g = 0; g < NT; ++g) headGroup[groupFirst[g]] = g;
+  std::vector<dlong> rowOfGroup((size_t)NT);
+  dlong NP = 0;
+  for (dlong g = 0; g < NT; ++g) NP += groupPos[g] ? 1 : 0;
+  dlong nextP = 0, nextM = NP;
+  for (dlong i = 0; i < n; ++i) {
+    const dlong g = headGroup[i];
+    if (g < 0) continue;
+    rowOfGroup[g] = groupPos[g] ? nextP++ : nextM++;
+  }
+  headGroup.clear();
+  headGroup.shrink_to_fit();
+  op->NrowsT = NT;
+  op->NrowsN = NP;
+
+  std::vector<dlong> rowOfEntry((size_t)n);
+  op->rowLabel.assign((size_t)NT, 0);
+#pragma omp parallel for
+  for (dlong i = 0; i < n; ++i) {
+    const dlong row = rowOfGroup[groupOfSorted[i]];
+    rowOfEntry[keys[i].idx] = row;
+    op->rowLabel[row] = keys[i].label;  // same value from every copy
+  }
+  keys.clear();
+  keys.shrink_to_fit();
+  groupOfSorted.clear();
+  groupOfSorted.shrink_to_fit();
+
+  // CSR "T": every copy; sweeping entries in column order keeps columns ascending inside a row
+  op->rowStartsT.assign((size_t)NT + 1, 0);
+  for (dlong i = 0; i < n; ++i) op->rowStartsT[rowOfEntry[i] + 1]++;
+  for (dlong r = 0; r < NT; ++r) op->rowStartsT[r + 1] += op->rowStartsT[r];
+  op->colIdsT.resize((size_t)n);
+  {
+    std::vector<dlong> fill(op->rowStartsT.begin(), op->rowStartsT.end() - 1);
+    for (dlong i = 0; i < n; ++i) op->colIdsT[fill[rowOfEntry[i]]++] = cols[i];
+  }
+  // CSR "N": positive copies only (libs/ogs/ogsOperator.cpp:620-643).  rowStartsN carries NrowsT+1
+  // entries (rows >= NrowsN are empty) so kernels may walk the T row partition over it.
+  if (op->kind == Signed) {
+    op->rowStartsN.assign((size_t)NT + 1, 0);
+    dlong nnzN = 0;
+    for (dlong i = 0; i < n; ++i)
+      if (ids[i] > 0) { op->rowStartsN[rowOfEntry[i] + 1]++; ++nnzN; }
+    for (dlong r = 0; r < NT; ++r) op->rowStartsN[r + 1] += op->rowStartsN[r];
+    op->nnzN = nnzN;
+    op->colIdsN.resize((size_t)nnzN);
+    std::vector<dlong> fill(op->rowStartsN.begin(), op->rowStartsN.end() - 1);
+    for (dlong i = 0; i < n; ++i)
+      if (ids[i] > 0) op->colIdsN[fill[rowOfEntry[i]]++] = cols[i];
+  } else {
+    op->nnzN = op->nnzT;
+    op->NrowsN = op->NrowsT;
+  }
+  return op;
+}
+
+}  // namespace
+
+void ogs_t::Free() {
+  if (packedEvent) { spn_event_destroy(packedEvent); packedEvent = nullptr; }
+  if (recvEvent) { spn_event_destroy(recvEvent); recvEvent = nullptr; }
+  commStream = nullptr;  // owned by the platform
+  gatherLocal = nullptr;
+  gatherHalo = nullptr;
+  for (auto& d : data) d = ogsExchangeData_t();
+  o_ownBuf.free();
+  o_sendBuf.free();
+  o_recvBuf.free();
+  N = Ngather = NlocalT = NlocalP = NhaloT = NhaloP = 0;
+  NgatherGlobal = 0;
+  on_device = false;
+  exchange_in_flight = false;
+}
+
+void ogs_t::AssertGatherDefined() const {
+  SPN_ABORT("Gather operation not well-defined.", !gather_defined);  // libs/ogs/ogsSetup.cpp:827-830
+}
+
+void ogs_t::SetupHost(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_, const bool unique_, const bool verbose) {
+  Free();
+  SetupPlan(N_, ids, comm_, kind_, unique_, verbose);
+}
+
+void ogs_t::Setup(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_, const Method /*method: Pairwise over NCCL only*/,
+                  const bool unique_, const bool verbose, platform_t& platform_) {
+  Free();
+  const timePoint_t start = Time();
+  platform = platform_;
+  SetupPlan(N_, ids, comm_, kind_, unique_, verbose);
+
+  // device copies (reference: ogsOperator_t ctor uploads, libs/ogs/ogsOperator.cpp:618-665)
+  gatherLocal->upload(platform, /*tile_plans=*/true);
+  gatherHalo->upload(platform, /*tile_plans=*/false);
+  for (int m = 0; m < 3; ++m) {
+    ogsExchangeData_t& d = data[m];
+    if (kind == Unsigned && m != Sym) {  // reference: data[NoTrans] = data[Trans] = data[Sym]
+      d.o_sendIds = data[Sym].o_sendIds;
+      d.o_cmbStarts = data[Sym].o_cmbStarts;
+      d.o_cmbIds = data[Sym].o_cmbIds;
+      continue;
+    }
+    if (d.Nsend) d.o_sendIds = platform.malloc<dlong>(d.sendIds);
+    if (d.Nrows) d.o_cmbStarts = platform.malloc<dlong>(d.cmbStarts);
+    if (d.Nrecv) d.o_cmbIds = platform.malloc<dlong>(d.cmbIds);
+  }
+  if (comm.size() > 1) {
+    commStream = platform.createStream();
+    SPN_CHECK(spn_event_create(&packedEvent));
+    SPN_CHECK(spn_event_create(&recvEvent));
+    comm.device();  // NCCL communicator: collective, every rank reaches this point
+  }
+  AllocBuffer(sizeof(dfloat));
+  on_device = true;
+
+  platform.finish();
+  comm.Barrier();
+  if (comm.rank() == 0 && verbose)
+    printf("ogs Setup Time: %g seconds.\n", ElapsedTime(start, Time()));
+}
+
+void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_, const bool unique_, const bool verbose) {
+  N = N_;
+  comm = comm_;
+  kind = kind_;
+  unique = unique_;
+  const int rank = comm.rank(), size = comm.size();
+
+  SPN_ABORT("Invalid ogs setup requested", (kind == Unsigned && unique) || (kind == Halo && unique));
+  SPN_ABORT("halo_t (Kind Halo) is outside the hot path and not provided", kind == Halo);
+
+  // ---- non-zero labels, in column order ----------------------------------------------------
+  dlong Nids = 0;
+  for (dlong n = 0; n < N; ++n) Nids += (ids[n] != 0) ? 1 : 0;
+  std::vector<dlong> colIds((size_t)Nids);
+  std::vector<hlong> baseIds((size_t)Nids);
+  {
+    dlong c = 0;
+    for (dlong n = 0; n < N; ++n)
+      if (ids[n] != 0) { colIds[c] = n; baseIds[c] = ids[n]; ++c; }
+  }
+
+  // ---- 1. directory round ------------------------------------------------------------------
+  std::vector<int> sendCounts(size, 0), sendOffsets(size + 1, 0), recvCounts(size, 0), recvOffsets(size + 1, 0);
+  for (dlong n = 0; n < Nids; ++n) sendCounts[habs(baseIds[n]) % size]++;
+  for (int r = 0; r < size; ++r) sendOffsets[r + 1] = sendOffsets[r] + sendCounts[r];
+  std::vector<dlong> sendPos((size_t)Nids);  // entry n sits at slot sendPos[n] of the send buffer (stable by dest)
+  std::vector<hlong> sendLabels((size_t)Nids);
+  {
+    std::vector<int> fill(sendOffsets.begin(), sendOffsets.end() - 1);
+    for (dlong n = 0; n < Nids; ++n) {
+      const int dst = (int)(habs(baseIds[n]) % size);
+      sendPos[n] = fill[dst]++;
+      sendLabels[sendPos[n]] = baseIds[n];
+    }
+  }
+  comm.Alltoall(sendCounts.data(), recvCounts.data());
+  for (int r = 0; r < size; ++r) recvOffsets[r + 1] = recvOffsets[r] + recvCounts[r];
+  const dlong recvN = recvOffsets[size];
+  std::vector<hlong> recvLabels((size_t)recvN);
+  comm.Alltoallv(sendLabels.data(), sendCounts.data(), sendOffsets.data(), recvLabels.data(), recvCounts.data(),
+                 recvOffsets.data());
+
+  // group the received copies by |label|; inside a group they stay in (source rank, source order)
+  std::vector<Key> keys((size_t)recvN);
+#pragma omp parallel for
+  for (dlong i = 0; i < recvN; ++i) keys[i] = Key{habs(recvLabels[i]), i};
+  __gnu_parallel::sort(keys.begin(), keys.end(), key_less);
+  auto rank_of = [&](dlong idx) {  // source rank of receive slot idx
+    return (int)(std::upper_bound(recvOffsets.begin(), recvOffsets.end(), (int)idx) - recvOffsets.begin()) - 1;
+  };
+
+  std::vector<int> recvShared((size_t)recvN, 0);
+  std::vector<std::vector<hlong>> reply(size);  // per source rank: [label, nranks, (rank*2+positive)...] per shared label
+  int is_unique = 1;
+  hlong NsharedLabels = 0;
+  {
+    std::vector<hlong> sharers;
+    for (dlong s = 0; s < recvN;) {
+      dlong e = s + 1;
+      while (e < recvN && keys[e].label == keys[s].label) ++e;
+      const hlong label = keys[s].label;
+      if (unique) {
+        // one positive copy per label (reference: random pick, libs/ogs/ogsSetup.cpp:364-382)
+        const dlong m = (dlong)(mix64((unsigned long long)label) % (unsigned long long)(e - s));
+        for (dlong i = s; i < e; ++i) recvLabels[keys[i].idx] = -label;
+        recvLabels[keys[s + m].idx] = label;
+      } else {
+        int positives = 0;
+        for (dlong i = s; i < e; ++i) positives += (recvLabels[keys[i].idx] > 0) ? 1 : 0;
+        if (positives != 1) is_unique = 0;
+      }
+      const int r0 = rank_of(keys[s].idx), r1 = rank_of(keys[e - 1].idx);
+      if (r0 != r1) {
+        ++NsharedLabels;
+        sharers.clear();
+        for (dlong i = s; i < e;) {
+          const int r = rank_of(keys[i].idx);
+          int pos = 0;
+          dlong j = i;
+          for (; j < e && rank_of(keys[j].idx) == r; ++j) pos |= (recvLabels[keys[j].idx] > 0) ? 1 : 0;
+          sharers.push_back((hlong)r * 2 + pos);
+          i = j;
+        }
+        for (hlong sp : sharers) {
+          std::vector<hlong>& out = reply[(int)(sp >> 1)];
+          out.push_back(label);
+          out.push_back((hlong)sharers.size());
+          out.insert(out.end(), sharers.begin(), sharers.end());
+        }
+        for (dlong i = s; i < e; ++i) recvShared[keys[i].idx] = 1;
+      }
+      s = e;
+    }
+  }
+  keys.clear();
+  keys.shrink_to_fit();
+
+  comm.Allreduce(is_unique, Comm::Min);
+  gather_defined = (is_unique == 1);
+  if (verbose) {
+    hlong total = NsharedLabels;
+    comm.Allreduce(total);
+    if (rank == 0) printf("ogs Setup: %lld unique labels shared.\n", total);
+  }
+
+  // answers back to the sources
+  std::vector<int> sharedOfSlot((size_t)Nids);
+  comm.Alltoallv(recvShared.data(), recvCounts.data(), recvOffsets.data(), sharedOfSlot.data(), sendCounts.data(),
+                 sendOffsets.data());
+  if (unique) {
+    comm.Alltoallv(recvLabels.data(), recvCounts.data(), recvOffsets.data(), sendLabels.data(), sendCounts.data(),
+                   sendOffsets.data());
+    for (dlong n = 0; n < Nids; ++n) {
+      baseIds[n] = sendLabels[sendPos[n]];
+      ids[colIds[n]] = baseIds[n];  // write the signs back (libs/ogs/ogsSetup.cpp:147-150)
+    }
+  }
+  recvLabels.clear();
+  recvLabels.shrink_to_fit();
+  recvShared.clear();
+  recvShared.shrink_to_fit();
+
+  // sharer lists of the shared labels this rank holds
+  std::vector<hlong> sharerStream;
+  {
+    std::vector<int> sc(size), so(size + 1, 0), rc(size), ro(size + 1, 0);
+    std::vector<hlong> flat;
+    for (int r = 0; r < size; ++r) {
+      sc[r] = (int)reply[r].size();
+      so[r + 1] = so[r] + sc[r];
+      flat.insert(flat.end(), reply[r].begin(), reply[r].end());
+    }
+    comm.Alltoall(sc.data(), rc.data());
+    for (int r = 0; r < size; ++r) ro[r + 1] = ro[r] + rc[r];
+    sharerStream.resize((size_t)ro[size]);
+    comm.Alltoallv(flat.data(), sc.data(), so.data(), sharerStream.data(), rc.data(), ro.data());
+  }
+
+  // ---- 2. split into local / halo entries and number the rows ---------------------------------
+  std::vector<hlong> localIds, haloIds;
+  std::vector<dlong> localCols, haloCols;
+  for (dlong n = 0; n < Nids; ++n) {
+    if (sharedOfSlot[sendPos[n]]) { haloIds.push_back(baseIds[n]); haloCols.push_back(colIds[n]); }
+    else { localIds.push_back(baseIds[n]); localCols.push_back(colIds[n]); }
+  }
+  gatherLocal = build_operator(kind, N, localIds, localCols);
+  gatherHalo = build_operator(kind, N, haloIds, haloCols);
+  NlocalT = gatherLocal->NrowsT;
+  NlocalP = gatherLocal->NrowsN;
+  NhaloT = gatherHalo->NrowsT;
+  NhaloP = gatherHalo->NrowsN;
+  Ngather = NlocalP + NhaloP;
+  NgatherGlobal = Ngather;
+  comm.Allreduce(NgatherGlobal);
+
+  // ---- 3. exchange plan -------------------------------------------------------------------------
+  // halo row of a label: rowLabel sorted once
+  std::vector<std::pair<hlong, dlong>> labelRow((size_t)NhaloT);
+  for (dlong h = 0; h < NhaloT; ++h) labelRow[h] = {gatherHalo->rowLabel[h], h};
+  std::sort(labelRow.begin(), labelRow.end());
+  auto row_of_label = [&](hlong label) {
+    auto it = std::lower_bound(labelRow.begin(), labelRow.end(), std::make_pair(label, (dlong)-1));
+    SPN_ABORT("ogs setup: shared label without a halo row", it == labelRow.end() || it->first != label);
+    return it->second;
+  };
+
+  struct Slot { int rank; hlong label; dlong row; };
+  std::vector<Slot> sends[3], recvs[3];
+  for (size_t p = 0; p < sharerStream.size();) {
+    const hlong label = sharerStream[p];
+    const int nr = (int)sharerStream[p + 1];
+    const dlong h = row_of_label(label);
+    const bool mePos = (h < NhaloP);
+    for (int q = 0; q < nr; ++q) {
+      const hlong sp = sharerStream[p + 2 + q];
+      const int r = (int)(sp >> 1);
+      const bool rPos = (sp & 1) != 0;
+      if (r == rank) {
+        SPN_ABORT("ogs setup: inconsistent positive flag", rPos != mePos);
+        continue;
+      }
+      const Slot s{r, label, h};
+      sends[Sym].push_back(s);
+      recvs[Sym].push_back(s);
+      if (mePos) sends[NoTrans].push_back(s);  // only positive copies send (ogsPairwise.cpp:315-345)
+      if (rPos) recvs[NoTrans].push_back(s);
+      if (rPos) sends[Trans].push_back(s);     // only towards the positive copy (ogsPairwise.cpp:347-377)
+      if (mePos) recvs[Trans].push_back(s);
+    }
+    p += 2 + (size_t)nr;
+  }
+  const dlong rowsP[3] = {NhaloT, NhaloP, NhaloP};  // Sym, NoTrans, Trans: rows contributing their own partial
+  const dlong rowsOut[3] = {NhaloT, NhaloT, NhaloP};
+  auto slot_less = [](const Slot& a, const Slot& b) { return a.rank < b.rank || (a.rank == b.rank && a.label < b.label); };
+  for (int m = 0; m < 3; ++m) {
+    ogsExchangeData_t& d = data[m];
+    const int src = (kind == Unsigned) ? (int)Sym : m;  // Unsigned: one plan for all modes
+    std::vector<Slot>& S = sends[src];
+    std::vector<Slot>& R = recvs[src];
+    if (m == src) {
+      std::sort(S.begin(), S.end(), slot_less);
+      std::sort(R.begin(), R.end(), slot_less);
+    }
+    d.Nsend = (dlong)S.size();
+    d.Nrecv = (dlong)R.size();
+    d.NrowsP = (kind == Unsigned) ? NhaloT : rowsP[m];
+    d.Nrows = (kind == Unsigned) ? NhaloT : rowsOut[m];
+    d.sendIds.resize(S.size());
+    d.recvRows.resize(R.size());
+    for (size_t i = 0; i < S.size(); ++i) {
+      d.sendIds[i] = S[i].row;
+      if (i == 0 || S[i].rank != S[i - 1].rank) {
+        d.sendRanks.push_back(S[i].rank);
+        d.sendOffsets.push_back((dlong)i);
+        d.sendCounts.push_back(0);
+      }
+      d.sendCounts.back()++;
+    }
+    for (size_t i = 0; i < R.size(); ++i) {
+      d.recvRows[i] = R[i].row;
+      if (i == 0 || R[i].rank != R[i - 1].rank) {
+        d.recvRanks.push_back(R[i].rank);
+        d.recvOffsets.push_back((dlong)i);
+        d.recvCounts.push_back(0);
+      }
+      d.recvCounts.back()++;
+    }
+    // receive slots of every output row, ascending slot == ascending source rank
+    d.cmbStarts.assign((size_t)d.Nrows + 1, 0);
+    for (dlong i = 0; i < d.Nrecv; ++i) {
+      SPN_ABORT("ogs setup: receive slot outside the output rows", d.recvRows[i] >= d.Nrows);
+      d.cmbStarts[d.recvRows[i] + 1]++;
+    }
+    for (dlong r = 0; r < d.Nrows; ++r) d.cmbStarts[r + 1] += d.cmbStarts[r];
+    d.cmbIds.resize((size_t)d.Nrecv);
+    std::vector<dlong> fill(d.cmbStarts.begin(), d.cmbStarts.end() - 1);
+    for (dlong i = 0; i < d.Nrecv; ++i) d.cmbIds[fill[d.recvRows[i]]++] = i;
+  }
+}
+
+}  // namespace ogs
+}  // namespace spn
