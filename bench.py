@@ -45,6 +45,11 @@ def bs8_bytes(Nt, Ng):
     return 4 * (Ng + 1) + 4 * Nt + 8 * Nt + 8 * Nt
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one BS8 launch at the headline size, from the ncu --set full
+# capture summarised in profiles/ (None until a capture at this size is committed)
+TRAFFIC_BS8 = None
+
+
 def bs6_bytes(Nt, Ng):
     """BS/BS6/src/bs6Run.cpp:60-63 (BS7 counts the same total: bs7Run.cpp:60-63)"""
     return 4 * (Ng + 1) + 4 * Nt + 8 * Nt + 8 * Ng
@@ -193,6 +198,7 @@ def cuda_time(fn, iters, warm, torch):
 
 def run_suite(torch, K, peak, ogs_ctx):
     """BS0-BS7 at the BASELINE.json sizes (BS8 is the headline and is added by the caller)."""
+    from streamparanumal_b200 import host
     out = {}
     dev = "cuda"
 
@@ -231,21 +237,22 @@ def run_suite(torch, K, peak, ogs_ctx):
     torch.cuda.synchronize()
     out["BS0 launch"] = {"us_per_launch": (time.perf_counter() - t0) / 1000 * 1e6}
     del Ap, r
-    # BS6 / BS7 on the headline mesh
-    plan, Nt, Ng, q = ogs_ctx
+    # BS6 / BS7 on the headline mesh, through ogs_t as bs6Run.cpp:47 / bs7Run.cpp:47 call it
+    ogs, Nt, Ng, q = ogs_ctx
     gq = torch.empty(Ng, dtype=torch.float64, device=dev)
-    add("BS6 gather", bs6_bytes(Nt, Ng), cuda_time(lambda: plan.gather(1, q, gq), 20, 5, torch), Ng)
-    add("BS7 scatter", bs6_bytes(Nt, Ng), cuda_time(lambda: plan.scatter(1, gq, q), 20, 5, torch), Ng)
+    add("BS6 gather", bs6_bytes(Nt, Ng), cuda_time(lambda: ogs.Gather(gq, q, 1, host.ADD, host.TRANS), 20, 5, torch), Ng)
+    add("BS7 scatter", bs6_bytes(Nt, Ng), cuda_time(lambda: ogs.Scatter(q, gq, 1, host.NOTRANS), 20, 5, torch), Ng)
     return out
 
 
 def run_b200(args):
+    import ctypes
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import spn_testutil as util
     from streamparanumal_b200 import kernels as K
-    from streamparanumal_b200 import _lib
+    from streamparanumal_b200 import _lib, host
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -256,54 +263,67 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: streamparanumal_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    _lib.kernel_lib()  # fail loudly if the sm_100a library is missing
+    lib = _lib.kernel_lib()  # fail loudly if the sm_100a library is missing
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peak, peak_src = measured_peak()
 
-    # ---- setup: mesh -> CSR (host, once; not timed — the reference does not time it either) ----
+    # ---- setup: box mesh labels -> ogs_t (host, once; not timed — the reference does not time it either:
+    #      mesh_t::Setup + ogs.Setup run before bs8_t::Run, BS/BS8/bs8Main.cpp:45-51) ----
     nx, p = args.nx, args.p
     t_setup = time.perf_counter()
-    ids = util.hex_ids(nx, nx, nx, p)
-    rs, ci = util.csr_from_ids(ids)
-    del ids
-    Nt, Ng = ci.size, rs.size - 1
-    d_rs, d_ci = (torch.from_numpy(x).cuda() for x in (rs, ci))
-    plan = K.OgsPlan(rs, d_rs, d_ci, Nt)  # device operator (ogsOperator_t ctor equivalent)
+    comm = host.Comm()  # RANK / WORLD_SIZE / MASTER_PORT: host collectives over local sockets, device data over NCCL
+    platform = host.Platform(comm, local_rank)
+    ids, nglobal = host.box_hex_ids(rank, world, nx, nx, nx, p)
+    ogs = host.Ogs(ids, comm, kind=host.SIGNED, unique=True, platform=platform)
     t_setup = time.perf_counter() - t_setup
-    q = torch.from_numpy(util.splitmix64(Nt, 3 + rank)).cuda()
+    Nt_local = ids.size
+    Nt, Ng = Nt_local * world, ogs.NgatherGlobal  # bs8Run.cpp:52-56: Nelements*Np summed over ranks, ogs.NgatherGlobal
+    assert Ng == nglobal, "ogs setup lost labels"
+    halo = ogs.exchange_info(host.SYM)
+    del ids
+    q = torch.from_numpy(util.splitmix64(Nt_local, 3 + rank)).cuda()
 
-    if world > 1:
-        raise SystemExit("multi-GPU BS8 (halo exchange) is not wired into bench.py yet")
+    step = lambda: ogs.GatherScatter(q, 1, host.ADD, host.SYM)  # mesh.ogs.GatherScatter(o_q, 1, ogs::Add, ogs::Sym)
 
-    step = lambda: plan.gather_scatter(1, q)
+    def timed(fn, steps, warm):
+        """`steps` calls of fn between barrier + device sync; CUDA events; max over ranks (seconds per call)"""
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3 / steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- timed region: device-resident ----
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    t_step = e0.elapsed_time(e1) * 1e-3 / args.steps
+    t_step = timed(step, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: host buffers through the C ABI (pinned host q -> H2D -> kernel -> D2H), every step ----
-    lib = _lib.kernel_lib()
-    import ctypes
-    nbytes = Nt * 8
+    # ---- e2e: host buffers through the C ABI (pinned host q -> H2D -> ogs_t::GatherScatter -> D2H), every step ----
+    nbytes = Nt_local * 8
     hq = ctypes.c_void_p()
     _lib.check(lib.spn_host_malloc(ctypes.byref(hq), nbytes), "host_malloc")
-    hq_np = np.ctypeslib.as_array(ctypes.cast(hq, ctypes.POINTER(ctypes.c_double)), shape=(Nt,))
-    hq_np[:] = util.splitmix64(Nt, 11)
+    hq_np = np.ctypeslib.as_array(ctypes.cast(hq, ctypes.POINTER(ctypes.c_double)), shape=(Nt_local,))
+    hq_np[:] = util.splitmix64(Nt_local, 11 + rank)
     st = torch.cuda.current_stream().cuda_stream
 
     def e2e_step():
@@ -312,41 +332,60 @@ def run_b200(args):
         _lib.check(lib.spn_memcpy_d2h(hq, q.data_ptr(), nbytes, st, 1), "d2h")
 
     e2e_steps = max(3, min(args.steps, 10))
-    t_e2e = cuda_time(e2e_step, e2e_steps, 2, torch)
+    t_e2e = timed(e2e_step, e2e_steps, 2)
     _lib.check(lib.spn_host_free(hq), "host_free")
 
+    bytes_step = bs8_bytes(Nt, Ng)          # whole job, counted as bs8Run.cpp:58-61 does
+    bytes_rank = bytes_step / world
+    # launches per call: interior gatherScatter; + halo gather/pack and combine/scatter (ours) when the mesh is partitioned
+    launches_per_step = 1 if world == 1 else 3
     line = {
         "metric": "BS8 gather+scatter throughput (DOFs/s, NgatherGlobal per call time)",
-        "value": Ng * world / t_step * 1e-9, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "value": Ng / t_step * 1e-9, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BS8 ogs gatherScatter(Add,Sym,K=1), hex p={p}, {nx}^3 elements per rank",
-                   "nx": nx, "p": p, "Nt_per_rank": Nt, "Ng_per_rank": Ng, "tiles": plan.Ntiles,
-                   "l2": "q (1.07 GB) + CSR (0.9 GB) per call exceed the 126 MB L2; no flush needed",
+        "config": {"workload": f"BS8 ogs_t::GatherScatter(Add,Sym,K=1), hex p={p}, {nx}^3 elements per rank "
+                               f"(mpirun -np {world} ./BS8 -nx {nx} -ny {nx} -nz {nx} -p {p})",
+                   "nx": nx, "p": p, "Nt_per_rank": Nt_local, "Nt": Nt, "Ng": Ng, "Ngather_rank0": ogs.Ngather,
+                   "tiles_rank0": ogs.local_tiles, "halo_rows_rank0": ogs.NhaloT, "halo_send_rank0": halo["Nsend"],
+                   "neighbours_rank0": halo["NranksSend"],
+                   "exchange": "none (one rank)" if world == 1 else "NCCL send/recv group on a comm stream, overlapped with the interior kernel",
+                   "l2": "q (1.07 GB) + ids (0.54 GB) per call exceed the 126 MB L2; no flush needed",
                    "host_setup_s": round(t_setup, 2)},
-        "effective_gbs": bs8_bytes(Nt, Ng) * world / t_step * 1e-9,
-        "roofline": {"bound": "hbm", "kernel": "ogs_tile_kernel<double,Add,GATHER_SCATTER>",
-                     "achieved": bs8_bytes(Nt, Ng) / t_step * 1e-9, "peak": peak, "peak_source": peak_src,
-                     "unit": "GB/s", "frac": bs8_bytes(Nt, Ng) / t_step * 1e-9 / peak,
-                     "frac_of_8TBs_nominal": bs8_bytes(Nt, Ng) / t_step * 1e-9 / 8000.0,
-                     "algorithmic_bytes_per_launch": bs8_bytes(Nt, Ng), "traffic": None},
-        "e2e": {"value": Ng * world / t_e2e * 1e-9, "unit": "GDOF/s", "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
-                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
-        "gpu_launches": args.steps,
+        "effective_gbs": bytes_step / t_step * 1e-9,
+        "roofline": {"bound": "hbm", "kernel": "ogs_tile_pf_kernel<double,Add,GATHER_SCATTER>",
+                     "achieved": bytes_rank / t_step * 1e-9, "peak": peak, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": bytes_rank / t_step * 1e-9 / peak,
+                     "frac_of_8TBs_nominal": bytes_rank / t_step * 1e-9 / 8000.0,
+                     "algorithmic_bytes_per_launch": bytes_rank,
+                     "basis": "per GPU: reference-counted bytes of one call / ranks / step time"
+                              + ("" if world == 1 else " (step = halo pack + interior kernel + exchange + halo combine)"),
+                     "traffic": TRAFFIC_BS8 if (world == 1 and nx == 64 and p == 7) else None},
+        "e2e": {"value": Ng / t_e2e * 1e-9, "unit": "GDOF/s", "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+                "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world},
+        "gpu_launches": args.steps * launches_per_step,
         "clocks": clocks,
     }
 
     if args.suite and world == 1:
-        line["suite"] = run_suite(torch, K, peak, (plan, Nt, Ng, q))
+        line["suite"] = run_suite(torch, K, peak, (ogs, Nt, Ng, q))
         line["suite"]["BS8 gatherScatter"] = {"ms": t_step * 1e3, "GB/s": line["effective_gbs"],
                                               "frac_of_measured_peak": line["roofline"]["frac"],
                                               "frac_of_8TBs": line["roofline"]["frac_of_8TBs_nominal"],
-                                              "GDOF/s": line["value"], "bytes": bs8_bytes(Nt, Ng)}
+                                              "GDOF/s": line["value"], "bytes": bytes_step}
 
-    if args.cpu_baseline and rank == 0:
+    if args.cpu_baseline and rank == 0 and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
         print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ogs.close()
+    platform.close()
+    comm.close()
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

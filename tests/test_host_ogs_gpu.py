@@ -1,0 +1,206 @@
+"""GPU parity of the C++ host layer (libspn_host.so: spn::ogs::ogs_t on a platform_t) — the
+reference-facing API of this path (include/ogs.hpp:216-341) driven exactly as BS6/BS7/BS8 drive it
+(BS/BS6/src/bs6Run.cpp:29-79, BS/BS7/src/bs7Run.cpp:29-79, BS/BS8/src/bs8Run.cpp:29-78).
+
+  * one rank: Gather / Scatter / GatherScatter (+ Start/Finish halves) on the device against the
+    oracle walking the same host plan (tests/ogs_sim.py), every Transpose mode, K in {1,3},
+    all four element types, masked (id 0) nodes;
+  * 2/4/8 ranks, one GPU each (skipped when the box has fewer GPUs): the NCCL pairwise exchange +
+    fused halo kernels against the same walk with a gloo exchange — bit-exact, because the fold
+    order (own partial, then ascending source rank: libs/ogs/ogsPairwise.cpp:214-232) is kept —
+    and the scalar NCCL allreduce behind norm/dot/rdotr at P>1.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+pytestmark = pytest.mark.gpu
+
+NP_OF = {"float64": np.float64, "float32": np.float32, "int32": np.int32, "int64": np.int64}
+
+
+def _values(n, dtype, seed):
+    import spn_testutil as util
+    dtype = np.dtype(dtype)
+    if np.issubdtype(dtype, np.floating):
+        return util.splitmix64(n, seed).astype(dtype)
+    return ((np.arange(n, dtype=np.int64) * 7919 + seed) % 23 - 11).astype(dtype)
+
+
+def _check_all_modes(ogs, plan, rank, K, dtype, dev):
+    """device ogs_t operations vs the oracle walk of the same plan; returns nothing, asserts"""
+    import ogs_sim
+    from streamparanumal_b200 import host
+    n = ogs.N
+    v = _values(n * K, dtype, 100 + rank)
+    ops = [host.ADD, host.MAX] if K == 1 else [host.ADD]
+    for op in ops:
+        for trans in (host.SYM, host.NOTRANS, host.TRANS):
+            d_v = torch.from_numpy(v.copy()).to(dev)
+            ogs.GatherScatter(d_v, K, op, trans)
+            exp = ogs_sim.gather_scatter(plan, v, K=K, op=op, trans=trans)
+            got = d_v.cpu().numpy()
+            assert np.array_equal(got, exp), f"GatherScatter op={op} trans={trans} K={K} {dtype}"
+    # Start / Finish halves with unrelated device work in between (include/ogs.hpp:130-140)
+    d_v = torch.from_numpy(v.copy()).to(dev)
+    other = torch.ones(1 << 16, device=dev)
+    ogs.GatherScatterStart(d_v, K, host.ADD, host.SYM)
+    other.mul_(2.0)
+    ogs.GatherScatterFinish(d_v, K, host.ADD, host.SYM)
+    assert np.array_equal(d_v.cpu().numpy(), ogs_sim.gather_scatter(plan, v, K=K, op=host.ADD, trans=host.SYM))
+
+    if not ogs.gather_defined:
+        return
+    # Gather: Trans reduces across ranks to the owner (BS6); NoTrans reads positive copies only
+    for trans in (host.TRANS, host.NOTRANS):
+        d_v = torch.from_numpy(v.copy()).to(dev)
+        d_gv = torch.zeros(max(ogs.Ngather, ogs.NlocalT + ogs.NhaloT) * K, dtype=d_v.dtype, device=dev)
+        ogs.Gather(d_gv, d_v, K, host.ADD, trans)
+        exp = ogs_sim.gather(plan, v, K=K, op=host.ADD, trans=trans)
+        m = ogs.Ngather * K
+        assert np.array_equal(d_gv.cpu().numpy()[:m], exp[:m]), f"Gather trans={trans} K={K} {dtype}"
+    # Scatter: NoTrans sends owner values to every copy (BS7); Trans writes positive copies only
+    gv = _values(max(ogs.Ngather, ogs.NlocalT + ogs.NhaloT) * K, dtype, 200 + rank)
+    for trans in (host.NOTRANS, host.TRANS):
+        d_gv = torch.from_numpy(gv.copy()).to(dev)
+        base = _values(n * K, dtype, 300 + rank)
+        d_v = torch.from_numpy(base.copy()).to(dev)
+        ogs.Scatter(d_v, d_gv, K, trans)
+        exp = ogs_sim.scatter(plan, gv, base, K=K, trans=trans)
+        assert np.array_equal(d_v.cpu().numpy(), exp), f"Scatter trans={trans} K={K} {dtype}"
+    # BS7 o BS6 == BS8: Scatter(NoTrans) of Gather(Trans) equals GatherScatter(Sym), bit for bit
+    # on integer-valued data (exact sums in any order)
+    vi = (((np.arange(n * K, dtype=np.int64) + 3 * rank) % 11) - 5).astype(dtype)
+    d_v = torch.from_numpy(vi.copy()).to(dev)
+    d_gv = torch.zeros(max(ogs.Ngather, ogs.NlocalT + ogs.NhaloT) * K, dtype=d_v.dtype, device=dev)
+    ogs.Gather(d_gv, d_v, K, host.ADD, host.TRANS)
+    d_w = torch.zeros_like(d_v)
+    ogs.Scatter(d_w, d_gv, K, host.NOTRANS)
+    ogs.GatherScatter(d_v, K, host.ADD, host.SYM)
+    ids = ogs.ids
+    part = np.repeat(ids != 0, K)
+    assert np.array_equal(d_w.cpu().numpy()[part], d_v.cpu().numpy()[part])
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32", "int32", "int64"])
+@pytest.mark.parametrize("K", [1, 3])
+def test_single_rank_ogs_t(dtype, K):
+    import ogs_sim
+    from streamparanumal_b200 import host
+    torch.cuda.set_device(0)
+    comm = host.Comm(0, 1)
+    platform = host.Platform(comm, 0)
+    ids, nglobal = host.box_hex_ids(0, 1, 3, 2, 2, 5)
+    ids[7::41] = 0  # masked nodes do not participate (libs/ogs/ogsSetup.cpp:120-131)
+    ogs = host.Ogs(ids, comm, kind=host.SIGNED, unique=True, platform=platform)
+    assert ogs.NhaloT == 0 and ogs.gather_defined
+    plan = ogs_sim.Plan(ogs)
+    _check_all_modes(ogs, plan, 0, K, NP_OF[dtype], "cuda:0")
+    ogs.close()
+    platform.close()
+    comm.close()
+
+
+def test_single_rank_bs8_config_shape():
+    """degree-7 hex (the BASELINE.json mesh family) through ogs_t: all-ones -> node multiplicity in {1,2,4,8}"""
+    from streamparanumal_b200 import host
+    torch.cuda.set_device(0)
+    comm = host.Comm(0, 1)
+    platform = host.Platform(comm, 0)
+    nx = 6
+    ids, nglobal = host.box_hex_ids(0, 1, nx, nx, nx, 7)
+    ogs = host.Ogs(ids, comm, kind=host.SIGNED, unique=True, platform=platform)
+    assert ogs.NgatherGlobal == nglobal == (nx * 7 + 1) ** 3
+    q = torch.ones(ids.size, dtype=torch.float64, device="cuda:0")
+    ogs.GatherScatter(q, 1, host.ADD, host.SYM)
+    mult = q.cpu().numpy()
+    assert set(np.unique(mult)) == {1.0, 2.0, 4.0, 8.0}
+    assert mult.sum() == sum(c * c for c in np.bincount(np.unique(np.abs(ids), return_inverse=True)[1]))
+    ogs.close()
+    platform.close()
+    comm.close()
+
+
+# ---- multi-rank -----------------------------------------------------------------------------------
+def _worker(rank, world, port, tmpdir, nx, ny, nz, p, K, dtype_name, kind_unique):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["LOCAL_RANK"] = str(rank)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ogs_sim
+        from streamparanumal_b200 import host
+        torch.cuda.set_device(rank)
+        dev = f"cuda:{rank}"
+        comm = host.Comm(rank, world, rendezvous=tmpdir)
+        platform = host.Platform(comm, rank)
+        ids, nglobal = host.box_hex_ids(rank, world, nx, ny, nz, p)
+        kind, unique = kind_unique
+        ogs = host.Ogs(ids, comm, kind=kind, unique=unique, platform=platform)
+        assert ogs.NhaloT > 0
+        if kind == host.SIGNED:
+            assert comm.allreduce(int(ogs.Ngather)) == nglobal == ogs.NgatherGlobal
+        plan = ogs_sim.Plan(ogs)
+        _check_all_modes(ogs, plan, rank, K, NP_OF[dtype_name], dev)
+
+        # all-ones -> multiplicity of every node in the GLOBAL mesh; total = sum over labels of copies^2
+        q = torch.ones(ids.size * K, dtype=torch.float64, device=dev)
+        for _ in range(3):  # repeated calls reuse the exchange buffers and events
+            q.fill_(1.0)
+            ogs.GatherScatter(q, K, host.ADD, host.SYM)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, np.abs(ogs.ids))
+        labels, counts = np.unique(np.concatenate(gathered), return_counts=True)
+        mult = counts[np.searchsorted(labels, np.abs(ogs.ids))]
+        assert np.array_equal(q.cpu().numpy(), np.repeat(mult, K).astype(np.float64))
+
+        # scalar allreduce behind dot / norm / rdotr (north_star; absent in the reference: SURVEY.md 2.4)
+        s = torch.full((2,), float(rank + 1), dtype=torch.float64, device=dev)
+        comm.allreduce_device(s)
+        assert s.cpu().tolist() == [world * (world + 1) / 2.0] * 2
+        torch.cuda.synchronize()
+        dist.barrier()
+        ogs.close()
+        platform.close()
+        comm.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+MULTI = [
+    # world, nx, ny, nz, p, K, dtype, (kind, unique)
+    (2, 3, 2, 2, 7, 1, "float64", (1, True)),
+    (2, 2, 2, 2, 3, 3, "float32", (1, True)),
+    (2, 2, 2, 2, 2, 1, "float64", (0, False)),
+    (4, 2, 2, 2, 7, 1, "float64", (1, True)),
+    (4, 2, 1, 2, 3, 2, "int64", (1, True)),
+    (8, 2, 2, 2, 7, 1, "float64", (1, True)),
+    (8, 1, 2, 1, 3, 2, "int32", (1, True)),
+]
+
+
+@pytest.mark.parametrize("world,nx,ny,nz,p,K,dtype,kind_unique", MULTI)
+def test_multirank_ogs_t_nccl(world, nx, ny, nz, p, K, dtype, kind_unique):
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")
+    with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
+        mp.spawn(_worker, args=(world, _free_port(), tmpdir, nx, ny, nz, p, K, dtype, kind_unique), nprocs=world, join=True)

@@ -50,6 +50,11 @@ def main():
     tgs = timeit(lambda: plan.gather_scatter(1, v), iters=50)
     print(f"tile plan: gather {tg*1e3:.3f} ms {b6/tg*1e-9:7.1f} GB/s | scatter {ts*1e3:.3f} ms {b6/ts*1e-9:7.1f} GB/s | "
           f"gatherScatter {tgs*1e3:.3f} ms {b8/tgs*1e-9:7.1f} GB/s {Ng/tgs*1e-9:6.1f} GDOF/s", flush=True)
+    plan_b = K.OgsPlan(rs, d_rs, d_ci, Nt, colIds=None)  # gatherScatter walks the gather tiles (first-appearance row order)
+    tb = timeit(lambda: plan_b.gather_scatter(1, v), iters=50)
+    print(f"gatherScatter without the sector-completing row order: {tb*1e3:.3f} ms {b8/tb*1e-9:7.1f} GB/s {Ng/tb*1e-9:6.1f} GDOF/s "
+          f"({plan_b.Ntiles} tiles)", flush=True)
+    plan_b.close()
     if os.environ.get("OGS_PROBE"):
         from streamparanumal_b200 import _lib
         w = torch.empty_like(v)
