@@ -23,6 +23,8 @@ using dlong = int;
 using hlong = long long int;
 
 class platform_t;
+class kernel_t;
+class properties_t;
 
 namespace detail {
 struct DeviceBlock {
@@ -157,6 +159,12 @@ class platform_t {
   void setStream(spn_stream_t s) { *state_->current = s; }
   spn_stream_t createStream();
   void finish() { SPN_CHECK(spn_stream_sync(*state_->current)); }  // device.finish()
+  const std::shared_ptr<spn_stream_t>& streamSlot() const { return state_->current; }
+
+  // platform.buildKernel(file, name, props) (include/platform.hpp:92-93): resolves the kernel name and
+  // its defines to a precompiled sm_100a entry point (host/kernel.cpp); "CUDA" is the only mode
+  kernel_t buildKernel(const std::string& fileName, const std::string& kernelName, const properties_t& props);
+  std::string mode() const { return "CUDA"; }  // platform.device.mode()
 
  private:
   struct State {

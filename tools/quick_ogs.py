@@ -50,27 +50,22 @@ def main():
     tgs = timeit(lambda: plan.gather_scatter(1, v), iters=50)
     print(f"tile plan: gather {tg*1e3:.3f} ms {b6/tg*1e-9:7.1f} GB/s | scatter {ts*1e3:.3f} ms {b6/ts*1e-9:7.1f} GB/s | "
           f"gatherScatter {tgs*1e3:.3f} ms {b8/tgs*1e-9:7.1f} GB/s {Ng/tgs*1e-9:6.1f} GDOF/s", flush=True)
-    plan_b = K.OgsPlan(rs, d_rs, d_ci, Nt, colIds=None)  # gatherScatter walks the gather tiles (first-appearance row order)
-    tb = timeit(lambda: plan_b.gather_scatter(1, v), iters=50)
-    print(f"gatherScatter without the sector-completing row order: {tb*1e3:.3f} ms {b8/tb*1e-9:7.1f} GB/s {Ng/tb*1e-9:6.1f} GDOF/s "
-          f"({plan_b.Ntiles} tiles)", flush=True)
-    plan_b.close()
-    if os.environ.get("OGS_PROBE"):
-        from streamparanumal_b200 import _lib
-        w = torch.empty_like(v)
-        t = timeit(lambda: plan.gather_scatter_to(1, v, w), iters=50)
-        print(f"probe out-of-place gs: {t*1e3:.3f} ms {b8/t*1e-9:7.1f} GB/s", flush=True)
-        for var in (2, 4, 6):
-            _lib.kernel_lib().spn_debug_set(0, var)
-            t = timeit(lambda: plan.gather_scatter(1, v), iters=50)
-            t2 = timeit(lambda: plan.gather_scatter_to(1, v, w), iters=50)
-            print(f"probe variant {var}: in-place {t*1e3:.3f} ms {b8/t*1e-9:7.1f} GB/s | out-of-place {t2*1e3:.3f} ms", flush=True)
-        _lib.kernel_lib().spn_debug_set(0, 0)
-        for probe in (8, 16, 0):
-            _lib.kernel_lib().spn_debug_set(1, probe)
-            t = timeit(lambda: plan.gather_scatter(1, v), iters=50)
-            tg2 = timeit(lambda: plan.gather(1, v, gv))
-            print(f"probe rounds {probe} (8: R=0, 16: R=7, 0: real): gs {t*1e3:.3f} ms {b8/t*1e-9:7.1f} GB/s | gather {tg2*1e3:.3f} ms {b6/tg2*1e-9:7.1f} GB/s", flush=True)
+    from streamparanumal_b200 import _lib
+    L = _lib.kernel_lib()
+    names = {0: "class tiles pipelined .cs stores", 2: "class tiles simple .cs", 4: "class tiles pipelined plain stores",
+             6: "class tiles simple plain stores", 1: "warp tiles (ogs_tile.cuh)"}
+    L.spn_debug_set(3, 1)
+    for sr in [int(x) for x in os.environ.get("OGS_SLICES", "65536").split(",")]:
+        L.spn_debug_set(2, sr)
+        pl = K.OgsPlan(rs, d_rs, d_ci, Nt, colIds=ci)
+        for var in (0, 2, 4, 6, 1):
+            L.spn_debug_set(0, var)
+            t = timeit(lambda: pl.gather_scatter(1, v), iters=50)
+            print(f"slice {sr:7d} variant {var} [{names[var]}]: {t*1e3:.3f} ms {b8/t*1e-9:7.1f} GB/s {Ng/t*1e-9:6.1f} GDOF/s", flush=True)
+        L.spn_debug_set(0, 0)
+        pl.close()
+    L.spn_debug_set(2, 65536)
+    L.spn_debug_set(3, 0)
     for lim in limits:
         bs = util.greedy_blocks(rs, lim)
         nb = bs.size - 1
