@@ -8,9 +8,9 @@ CSRC      := streamparanumal_b200/csrc
 LIBDIR    := streamparanumal_b200/lib
 
 KERNEL_SRCS := $(CSRC)/runtime.cu $(CSRC)/stream_abi.cu $(CSRC)/ogs_abi.cu $(CSRC)/ogs_plan.cu $(CSRC)/ogs_halo.cu
-KERNEL_HDRS := $(CSRC)/common.cuh $(CSRC)/stream_kernels.cuh $(CSRC)/ogs_kernels.cuh $(CSRC)/ogs_pipe.cuh $(CSRC)/ogs_tile.cuh include/spn_b200.h
+KERNEL_HDRS := $(CSRC)/common.cuh $(CSRC)/stream_kernels.cuh $(CSRC)/ogs_kernels.cuh $(CSRC)/ogs_pipe.cuh $(CSRC)/ogs_tile.cuh $(CSRC)/ogs_ctile.cuh include/spn_b200.h
 
-all: $(LIBDIR)/libspn_b200.so $(LIBDIR)/libspn_b200_comm.so $(LIBDIR)/libspn_host.so
+all: $(LIBDIR)/libspn_b200.so $(LIBDIR)/libspn_b200_comm.so $(LIBDIR)/libspn_host.so bs
 
 $(LIBDIR)/libspn_b200.so: $(KERNEL_SRCS) $(KERNEL_HDRS)
 	@mkdir -p $(LIBDIR)
@@ -22,20 +22,36 @@ $(LIBDIR)/libspn_b200_comm.so: $(CSRC)/comm_nccl.cu include/spn_b200.h
 
 # C++ host layer (mirror of the reference's ogs / platform / comm API) + its C binding
 HOST      := streamparanumal_b200/host
-HOST_SRCS := $(HOST)/comm.cpp $(HOST)/platform.cpp $(HOST)/ogs_setup.cpp $(HOST)/ogs_ops.cpp $(HOST)/mesh.cpp $(HOST)/capi.cpp
-HOST_HDRS := $(HOST)/comm.hpp $(HOST)/platform.hpp $(HOST)/ogs.hpp include/spn_b200.h include/spn_host.h
+HOST_SRCS := $(HOST)/comm.cpp $(HOST)/platform.cpp $(HOST)/ogs_setup.cpp $(HOST)/ogs_ops.cpp $(HOST)/mesh.cpp $(HOST)/kernel.cpp $(HOST)/capi.cpp
+HOST_HDRS := $(HOST)/comm.hpp $(HOST)/platform.hpp $(HOST)/ogs.hpp $(HOST)/kernel.hpp include/spn_b200.h include/spn_host.h
 CXXFLAGS  := -O2 -g -std=c++17 -fPIC -fopenmp -Wall -Iinclude -I$(HOST)
 $(LIBDIR)/libspn_host.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/libspn_b200.so $(LIBDIR)/libspn_b200_comm.so
 	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) -L$(LIBDIR) -lspn_b200 -lspn_b200_comm -Wl,-rpath,'$$ORIGIN'
+
+# BS0..BS8 executables (reference CLI and output lines) and the local rank launcher (mpirun stand-in)
+BSDIR     := streamparanumal_b200/bs
+BINDIR    := streamparanumal_b200/bin
+BS_BINS   := $(foreach n,0 1 2 3 4 5 6 7 8,$(BINDIR)/BS$(n)) $(BINDIR)/spnrun
+bs: $(BS_BINS)
+BS_LINK   := -L$(LIBDIR) -lspn_host -lspn_b200 -lspn_b200_comm -Wl,-rpath,'$$ORIGIN/../lib'
+$(BINDIR)/BS0 $(BINDIR)/BS1 $(BINDIR)/BS2 $(BINDIR)/BS3 $(BINDIR)/BS4 $(BINDIR)/BS5: $(BSDIR)/bs_stream.cpp $(BSDIR)/settings.hpp $(LIBDIR)/libspn_host.so
+	@mkdir -p $(BINDIR)
+	$(CXX) $(CXXFLAGS) -fPIE -I$(BSDIR) -DSPN_BS=$(subst $(BINDIR)/BS,,$@) -o $@ $(BSDIR)/bs_stream.cpp $(BS_LINK)
+$(BINDIR)/BS6 $(BINDIR)/BS7 $(BINDIR)/BS8: $(BSDIR)/bs_ogs.cpp $(BSDIR)/settings.hpp $(LIBDIR)/libspn_host.so
+	@mkdir -p $(BINDIR)
+	$(CXX) $(CXXFLAGS) -fPIE -I$(BSDIR) -DSPN_BS=$(subst $(BINDIR)/BS,,$@) -o $@ $(BSDIR)/bs_ogs.cpp $(BS_LINK)
+$(BINDIR)/spnrun: $(BSDIR)/spnrun.cpp
+	@mkdir -p $(BINDIR)
+	$(CXX) -O2 -std=c++17 -Wall -o $@ $(BSDIR)/spnrun.cpp
 
 ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/stream_abi.cu 2>&1 | grep -E "Compiling|registers|spill"
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /dev/null $(CSRC)/ogs_abi.cu 2>&1 | grep -E "Compiling|registers|spill"
 
 clean:
-	rm -rf $(LIBDIR)/*.so build
+	rm -rf $(LIBDIR)/*.so $(BINDIR) build
 
-.PHONY: all clean ptxas-info
+.PHONY: all clean ptxas-info bs
 
 # ---- tuning tools (run on the GPU box) ----------------------------------------------
 tune: build/tune_stream

@@ -1,0 +1,111 @@
+"""The BS0..BS8 executables (streamparanumal_b200/bs): the reference command line and output lines
+(BS/BS*/src/bs*Run.cpp, bs*Settings.cpp) on the native backend.  CPU part: flag handling and the
+no-fallback rule; GPU part: every executable runs and prints the reference's line format."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "streamparanumal_b200", "bin")
+NUM = r"[-+0-9.eE]+"
+
+
+def run(args, timeout=300):
+    return subprocess.run(args, capture_output=True, text=True, timeout=timeout)
+
+
+def test_executables_are_built():
+    for n in range(9):
+        assert os.access(os.path.join(BIN, f"BS{n}"), os.X_OK), "run `make` first"
+    assert os.access(os.path.join(BIN, "spnrun"), os.X_OK)
+
+
+def test_unknown_flag_and_bad_value_abort():
+    r = run([os.path.join(BIN, "BS5"), "--nonsense"])
+    assert r.returncode != 0 and "Unrecognized setting" in r.stderr
+    r = run([os.path.join(BIN, "BS8"), "-p", "16"])           # degree is limited to 1..15 (meshSettings.cpp:45-49)
+    assert r.returncode != 0 and "not valid" in r.stderr
+    r = run([os.path.join(BIN, "BS1"), "-b"])
+    assert r.returncode != 0 and "Missing value" in r.stderr
+
+
+def test_only_cuda_mode_exists():
+    for mode in ("Serial", "OpenMP", "HIP", "OpenCL"):
+        r = run([os.path.join(BIN, "BS1"), "-m", mode, "-b", "1024"])
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_help_lists_reference_flags():
+    r = run([os.path.join(BIN, "BS1"), "--help"])
+    assert r.returncode == 0
+    for flag in ("-m", "--mode", "-b", "--bytes", "-bmin", "-bmax", "-s", "--bstep", "-v", "-d", "-pl"):
+        assert flag in r.stdout
+    r = run([os.path.join(BIN, "BS6"), "--help"])
+    for flag in ("-e", "--elements", "-nx", "--dimx", "-ny", "-nz", "-p", "--degree"):
+        assert flag in r.stdout
+    r = run([os.path.join(BIN, "BS0"), "--help"])
+    for flag in ("-n", "--Nlaunch", "-nmin", "-nmax", "--step"):
+        assert flag in r.stdout
+
+
+def test_no_device_no_result():
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    r = run([os.path.join(BIN, "BS5"), "-b", "4096"])
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    r = run([os.path.join(BIN, "spnrun"), "-np", "2", os.path.join(BIN, "BS8"), "-nx", "2", "-ny", "2", "-nz", "2"])
+    assert r.returncode != 0
+
+
+def test_spnrun_sets_ranks():
+    r = run([os.path.join(BIN, "spnrun"), "-np", "3", "/bin/sh", "-c", "echo rank=$SPN_RANK/$SPN_SIZE local=$LOCAL_RANK"])
+    assert r.returncode == 0
+    assert sorted(r.stdout.split()) == sorted(f"rank={i}/3 local={i}".split()[j] for i in range(3) for j in range(2))
+    r = run([os.path.join(BIN, "spnrun"), "-np", "2", "/bin/sh", "-c", "exit $((SPN_RANK+3))"])
+    assert r.returncode in (3, 4)
+
+
+@pytest.mark.gpu
+def test_stream_executables_print_reference_lines():
+    titles = {1: "Copy", 2: "AXPY", 3: "Norm", 4: "Dot", 5: "CG Update"}
+    for n, title in titles.items():
+        r = run([os.path.join(BIN, f"BS{n}"), "-b", str(48 << 20)])
+        assert r.returncode == 0, r.stderr
+        m = re.fullmatch(rf"BS{n} = \[(\d+) ({NUM}) ({NUM}) +({NUM})\]; %{title} \[DOFs, elapsed, DOFs/s, BW \(GB/s\)\]\n", r.stdout)
+        assert m, r.stdout
+        per_entry = {1: 16, 2: 24, 3: 8, 4: 16, 5: 24}[n]
+        assert int(m.group(1)) == (48 << 20) // per_entry
+        assert float(m.group(4)) > 100.0   # GB/s: a B200, not a host loop
+    # sweep form
+    r = run([os.path.join(BIN, "BS1"), "-bmin", "1048576", "-bmax", "4194304", "-s", "1048576"])
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().split("\n")
+    assert lines[0] == "%Copy [DOFs, elapsed, DOFs/s, BW (GB/s)]" and lines[1] == "BS1 = ["
+    assert len(lines) == 2 + 4 and lines[-1].endswith("]; %Copy [DOFs, elapsed, DOFs/s, BW (GB/s)]")
+    r = run([os.path.join(BIN, "BS0"), "-n", "50"])
+    assert r.returncode == 0 and re.match(rf"BS0 = \[50 {NUM} {NUM}\]; %Launch Latency", r.stdout), r.stdout
+
+
+@pytest.mark.gpu
+def test_ogs_executables_print_reference_lines():
+    what = {6: "Gather", 7: "Scatter", 8: "GatherScatter"}
+    for n, name in what.items():
+        r = run([os.path.join(BIN, f"BS{n}"), "-nx", "8", "-ny", "8", "-nz", "8", "-p", "7"])
+        assert r.returncode == 0, r.stderr
+        m = re.fullmatch(rf"BS{n} = \[7, (\d+), ({NUM}), ({NUM}), +({NUM}), +({NUM})\]; % {name} \[N, DOFs, elapsed, "
+                         rf"DOFs/\(ranks\*s\), avg BW \(GB/s\), avg GFLOPs\] \n", r.stdout)
+        assert m, r.stdout
+        assert int(m.group(1)) == (8 * 7 + 1) ** 3
+
+
+@pytest.mark.gpu
+def test_bs8_two_ranks_over_spnrun():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = run([os.path.join(BIN, "spnrun"), "-np", "2", os.path.join(BIN, "BS8"), "-nx", "8", "-ny", "8", "-nz", "8", "-p", "7"])
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"BS8 = \[7, (\d+),", r.stdout)
+    assert m and int(m.group(1)) == (2 * 8 * 7 + 1) * (8 * 7 + 1) ** 2
