@@ -70,6 +70,11 @@ int spn_host_ogs_halo_labels(spn_host_ogs_t ogs, const long long** ptr, long lon
 int spn_host_ogs_gather_scatter(spn_host_ogs_t ogs, void* d_v, int k, int type, int op, int trans);
 int spn_host_ogs_gather_scatter_start(spn_host_ogs_t ogs, void* d_v, int k, int type, int op, int trans);
 int spn_host_ogs_gather_scatter_finish(spn_host_ogs_t ogs, void* d_v, int k, int type, int op, int trans);
+/* host-buffer gather+scatter (the reference's host-memory overload, include/ogs.hpp:251-256): h_v is PINNED host memory
+ * (spn_host_malloc) of N*k entries.  start enqueues H2D -> GatherScatter -> D2H and returns; finish blocks until h_v holds the
+ * result.  Up to two operations may be in flight, so the next upload overlaps the previous download. */
+int spn_host_ogs_gather_scatter_host_start(spn_host_ogs_t ogs, void* h_v, int k, int type, int op, int trans);
+int spn_host_ogs_gather_scatter_host_finish(spn_host_ogs_t ogs, void* h_v);
 int spn_host_ogs_gather(spn_host_ogs_t ogs, void* d_gv, const void* d_v, int k, int type, int op, int trans);
 int spn_host_ogs_scatter(spn_host_ogs_t ogs, void* d_v, const void* d_gv, int k, int type, int trans);
 

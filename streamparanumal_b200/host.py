@@ -43,6 +43,8 @@ _HOST_SIGNATURES = {
     "spn_host_ogs_gather_scatter": [c_void_p, c_void_p, c_int, c_int, c_int, c_int],
     "spn_host_ogs_gather_scatter_start": [c_void_p, c_void_p, c_int, c_int, c_int, c_int],
     "spn_host_ogs_gather_scatter_finish": [c_void_p, c_void_p, c_int, c_int, c_int, c_int],
+    "spn_host_ogs_gather_scatter_host_start": [c_void_p, c_void_p, c_int, c_int, c_int, c_int],
+    "spn_host_ogs_gather_scatter_host_finish": [c_void_p, c_void_p],
     "spn_host_ogs_gather": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int],
     "spn_host_ogs_scatter": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int],
 }
@@ -203,6 +205,14 @@ class Ogs:
     def GatherScatterFinish(self, v, k=1, op=ADD, trans=SYM):
         self._sync_stream()
         _check(host_lib().spn_host_ogs_gather_scatter_finish(self._h, v.data_ptr(), k, self._type(v), op, trans), "GatherScatterFinish")
+
+    def HostGatherScatterStart(self, h_ptr, type, k=1, op=ADD, trans=SYM):
+        """h_ptr: address of a PINNED host vector (spn_host_malloc); enqueues H2D -> GatherScatter -> D2H and returns"""
+        self._sync_stream()
+        _check(host_lib().spn_host_ogs_gather_scatter_host_start(self._h, h_ptr, k, type, op, trans), "HostGatherScatterStart")
+
+    def HostGatherScatterFinish(self, h_ptr):
+        _check(host_lib().spn_host_ogs_gather_scatter_host_finish(self._h, h_ptr), "HostGatherScatterFinish")
 
     def Gather(self, gv, v, k=1, op=ADD, trans=TRANS):
         self._sync_stream()

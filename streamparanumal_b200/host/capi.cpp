@@ -178,6 +178,14 @@ int spn_host_ogs_gather_scatter_finish(spn_host_ogs_t h, void* v, int k, int typ
   if (!h) return SPN_ERR_INVALID_ARGUMENT;
   return guarded([&] { h->ogs.GatherScatterFinish(v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans); });
 }
+int spn_host_ogs_gather_scatter_host_start(spn_host_ogs_t h, void* h_v, int k, int type, int op, int trans) {
+  if (!h) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { h->ogs.HostGatherScatterStart(h_v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans); });
+}
+int spn_host_ogs_gather_scatter_host_finish(spn_host_ogs_t h, void* h_v) {
+  if (!h) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { h->ogs.HostGatherScatterFinish(h_v); });
+}
 int spn_host_ogs_gather(spn_host_ogs_t h, void* gv, const void* v, int k, int type, int op, int trans) {
   if (!h) return SPN_ERR_INVALID_ARGUMENT;
   return guarded([&] {

@@ -127,6 +127,24 @@ class ogs_t {
   void ScatterStart(void* o_v, const void* o_gv, int k, Type type, Transpose trans);
   void ScatterFinish(void* o_v, const void* o_gv, int k, Type type, Transpose trans);
 
+  // ---- host-buffer operation (the reference's host-memory overloads, include/ogs.hpp:251-267 on memory<T>, run
+  //      on the CPU; here the data is staged through the GPU).  Start enqueues  H2D -> GatherScatter -> D2H  of
+  //      h_v (pinned host memory, platform.hostMalloc) on dedicated copy streams and returns at once; Finish
+  //      waits until h_v holds the result.  Two operations may be in flight (double-buffered device staging), so
+  //      the upload of the next vector overlaps the download of the previous one (PCIe is full duplex). ----
+  void HostGatherScatterStart(void* h_v, int k, Type type, Op op, Transpose trans);
+  void HostGatherScatterFinish(void* h_v);
+  template <typename T> void GatherScatterStart(pinnedMemory<T> h_v, const int k, const Op op, const Transpose trans) {
+    HostGatherScatterStart(h_v.ptr(), k, ogsType<T>::get(), op, trans);
+  }
+  template <typename T> void GatherScatterFinish(pinnedMemory<T> h_v, const int, const Op, const Transpose) {
+    HostGatherScatterFinish(h_v.ptr());
+  }
+  template <typename T> void GatherScatter(pinnedMemory<T> h_v, const int k, const Op op, const Transpose trans) {
+    HostGatherScatterStart(h_v.ptr(), k, ogsType<T>::get(), op, trans);
+    HostGatherScatterFinish(h_v.ptr());
+  }
+
   // ---- the reference's signatures (include/ogs.hpp:251-341) ----
   template <typename T> void GatherScatter(deviceMemory<T> o_v, const int k, const Op op, const Transpose trans) {
     GatherScatterStart(o_v, k, op, trans);
@@ -170,6 +188,17 @@ class ogs_t {
   spn_stream_t commStream = nullptr;
   spn_event_t packedEvent = nullptr, recvEvent = nullptr;
   bool exchange_in_flight = false;
+
+  // staging of the host-buffer operations
+  struct HostStage {
+    deviceMemory<char> o_buf;
+    spn_event_t h2dDone = nullptr, computeDone = nullptr, d2hDone = nullptr;
+    void* h_v = nullptr;
+    bool busy = false;
+  };
+  HostStage stage[2];
+  int nextStage = 0;
+  spn_stream_t h2dStream = nullptr, d2hStream = nullptr;
 };
 
 }  // namespace ogs

@@ -183,6 +183,52 @@ void ogs_t::GatherScatterFinish(void* o_v, int k, Type type, Op op, Transpose tr
 }
 
 // ---------------------------------------------------------------------------------------------
+// GatherScatter on a pinned host vector: H2D | device operation | D2H on three streams, two stages
+// ---------------------------------------------------------------------------------------------
+void ogs_t::HostGatherScatterStart(void* h_v, int k, Type type, Op op, Transpose trans) {
+  SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
+  SPN_ABORT("HostGatherScatterStart: null host vector", h_v == nullptr && N > 0);
+  HostStage& s = stage[nextStage];
+  SPN_ABORT("HostGatherScatterStart: two host-buffer operations are already in flight (call Finish first)", s.busy);
+  nextStage ^= 1;
+  const size_t bytes = (size_t)N * (size_t)k * Sizeof(type);
+  if (!h2dStream) {
+    h2dStream = platform.createStream();
+    d2hStream = platform.createStream();
+  }
+  if (!s.h2dDone) {
+    SPN_CHECK(spn_event_create(&s.h2dDone));
+    SPN_CHECK(spn_event_create(&s.computeDone));
+    SPN_CHECK(spn_event_create(&s.d2hDone));
+  }
+  if (s.o_buf.size() < bytes) s.o_buf = platform.malloc<char>(bytes);
+  spn_stream_t cur = platform.getStream();
+  if (bytes) SPN_CHECK(spn_memcpy_h2d(s.o_buf.ptr(), h_v, bytes, h2dStream, 1));
+  SPN_CHECK(spn_event_record(s.h2dDone, h2dStream));
+  SPN_CHECK(spn_stream_wait_event(cur, s.h2dDone));
+  GatherScatterStart(s.o_buf.ptr(), k, type, op, trans);
+  GatherScatterFinish(s.o_buf.ptr(), k, type, op, trans);
+  SPN_CHECK(spn_event_record(s.computeDone, cur));
+  SPN_CHECK(spn_stream_wait_event(d2hStream, s.computeDone));
+  if (bytes) SPN_CHECK(spn_memcpy_d2h(h_v, s.o_buf.ptr(), bytes, d2hStream, 1));
+  SPN_CHECK(spn_event_record(s.d2hDone, d2hStream));
+  s.h_v = h_v;
+  s.busy = true;
+}
+
+void ogs_t::HostGatherScatterFinish(void* h_v) {
+  for (HostStage& s : stage) {
+    if (s.busy && s.h_v == h_v) {
+      SPN_CHECK(spn_event_sync(s.d2hDone));
+      s.busy = false;
+      s.h_v = nullptr;
+      return;
+    }
+  }
+  SPN_ABORT("HostGatherScatterFinish: no operation in flight on this host vector", true);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Gather (libs/ogs/ogs.cpp:206-301): o_gv = [NlocalT local rows | NhaloP owned halo rows]
 // ---------------------------------------------------------------------------------------------
 void ogs_t::GatherStart(void* o_gv, const void* o_v, int k, Type type, Op op, Transpose trans) {

@@ -142,6 +142,15 @@ void ogs_t::Free() {
   if (packedEvent) { spn_event_destroy(packedEvent); packedEvent = nullptr; }
   if (recvEvent) { spn_event_destroy(recvEvent); recvEvent = nullptr; }
   commStream = nullptr;  // owned by the platform
+  for (HostStage& st : stage) {
+    if (st.busy) spn_event_sync(st.d2hDone);
+    if (st.h2dDone) spn_event_destroy(st.h2dDone);
+    if (st.computeDone) spn_event_destroy(st.computeDone);
+    if (st.d2hDone) spn_event_destroy(st.d2hDone);
+    st = HostStage();
+  }
+  nextStage = 0;
+  h2dStream = d2hStream = nullptr;  // owned by the platform
   gatherLocal = nullptr;
   gatherHalo = nullptr;
   for (auto& d : data) d = ogsExchangeData_t();

@@ -57,6 +57,37 @@ def _check_all_modes(ogs, plan, rank, K, dtype, dev):
     ogs.GatherScatterFinish(d_v, K, host.ADD, host.SYM)
     assert np.array_equal(d_v.cpu().numpy(), ogs_sim.gather_scatter(plan, v, K=K, op=host.ADD, trans=host.SYM))
 
+    # host-buffer form (pinned host vector staged through the GPU; two operations in flight)
+    if K == 1 or np.dtype(dtype) == np.float64:
+        import ctypes
+        from streamparanumal_b200 import _lib, kernels
+        lib = _lib.kernel_lib()
+        npdt = np.dtype(dtype)
+        hp, hv = [], []
+        for i in range(2):
+            ptr = ctypes.c_void_p()
+            _lib.check(lib.spn_host_malloc(ctypes.byref(ptr), max(1, n * K * npdt.itemsize)), "host_malloc")
+            hp.append(ptr)
+            arr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_byte)), shape=(max(1, n * K * npdt.itemsize),))
+            hv.append(arr[: n * K * npdt.itemsize].view(npdt))
+        inputs = [v, _values(n * K, dtype, 400 + rank)]
+        for i in range(2):
+            hv[i][:] = inputs[i]
+        tcode = kernels.ogs_type(torch.from_numpy(np.empty(0, dtype=npdt)))
+        ogs.HostGatherScatterStart(hp[0], tcode, K, host.ADD, host.SYM)
+        ogs.HostGatherScatterStart(hp[1], tcode, K, host.ADD, host.SYM)
+        with pytest.raises(RuntimeError):
+            ogs.HostGatherScatterStart(hp[0], tcode, K, host.ADD, host.SYM)  # a third one must be refused
+        ogs.HostGatherScatterFinish(hp[0])
+        ogs.HostGatherScatterFinish(hp[1])
+        for i in range(2):
+            assert np.array_equal(hv[i], ogs_sim.gather_scatter(plan, inputs[i], K=K, op=host.ADD, trans=host.SYM)), \
+                f"host-buffer GatherScatter #{i} K={K} {dtype}"
+        with pytest.raises(RuntimeError):
+            ogs.HostGatherScatterFinish(hp[0])  # nothing in flight any more
+        for ptr in hp:
+            _lib.check(lib.spn_host_free(ptr), "host_free")
+
     if not ogs.gather_defined:
         return
     # Gather: Trans reduces across ranks to the owner (BS6); NoTrans reads positive copies only

@@ -3,7 +3,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_n$N.txt 2>&1
-timeout 900 python -m pytest tests/test_host_ogs_gpu.py -m gpu -x -q > gpurun_out/pytest_n$N.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_n$N.log
+timeout 900 python -m pytest tests/test_host_ogs_gpu.py tests/test_bs_executables.py -m gpu -x -q > gpurun_out/pytest_n$N.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_n$N.log
 tail -5 gpurun_out/pytest_n$N.log
 for n in $(seq 1 8); do
   if [ $n -le $N ] && { [ $n -eq 2 ] || [ $n -eq 4 ] || [ $n -eq 8 ]; }; then
