@@ -366,7 +366,7 @@ def run_b200(args):
     bytes_step = bs8_bytes(Nt, Ng)          # whole job, counted as bs8Run.cpp:58-61 does
     bytes_rank = bytes_step / world
     # launches per call: interior gatherScatter; + halo gather/pack and combine/scatter (ours) when the mesh is partitioned
-    launches_per_step = 1 if world == 1 else 3
+    launches_per_step = 1 if world == 1 else 3  # halo gather+pack, interior gatherScatter, halo combine+scatter
     line = {
         "metric": "BS8 gather+scatter throughput (DOFs/s, NgatherGlobal per call time)",
         "value": Ng / t_step * 1e-9, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -377,7 +377,9 @@ def run_b200(args):
                    "nx": nx, "p": p, "Nt_per_rank": Nt_local, "Nt": Nt, "Ng": Ng, "Ngather_rank0": ogs.Ngather,
                    "tiles_rank0": ogs.local_tiles, "halo_rows_rank0": ogs.NhaloT, "halo_send_rank0": halo["Nsend"],
                    "neighbours_rank0": halo["NranksSend"],
-                   "exchange": "none (one rank)" if world == 1 else "NCCL send/recv group on a comm stream, overlapped with the interior kernel",
+                   "exchange": "none (one rank)" if world == 1 else (
+                       "peer memory: the halo pack kernel stores partials straight into the neighbours' receive buffers over NVLink (P2P, CUDA IPC) and raises flags; the combine kernel waits on them after the interior kernel"
+                       if ogs.peer_exchange else "NCCL send/recv group on a comm stream, overlapped with the interior kernel"),
                    "l2": "q (1.07 GB) + ids (0.54 GB) per call exceed the 126 MB L2; no flush needed",
                    "host_setup_s": round(t_setup, 2)},
         "effective_gbs": bytes_step / t_step * 1e-9,
@@ -387,7 +389,7 @@ def run_b200(args):
                      "frac_of_8TBs_nominal": bytes_rank / t_step * 1e-9 / 8000.0,
                      "algorithmic_bytes_per_launch": bytes_rank,
                      "basis": "per GPU: reference-counted bytes of one call / ranks / step time"
-                              + ("" if world == 1 else " (step = halo pack + interior kernel + exchange + halo combine)"),
+                              + ("" if world == 1 else " (step = halo pack [+ exchange] + interior kernel + halo combine)"),
                      "traffic": TRAFFIC_BS8 if (world == 1 and nx == 64 and p == 7) else None},
         "e2e": {"value": Ng / t_e2e * 1e-9, "unit": "GDOF/s", "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
                 "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,

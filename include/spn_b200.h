@@ -67,6 +67,9 @@ int spn_get_device(int* device_id);
 int spn_device_sm_count(int* sms);
 int spn_device_sync(void);
 int spn_stream_create(spn_stream_t* stream);      /* device.createStream(), libs/ogs/ogsSetup.cpp:103-104 */
+/* high != 0: highest priority the device offers — pending blocks of this stream are scheduled before those of
+ * normal streams (used for the halo kernels, which must slip in between the blocks of the interior operator) */
+int spn_stream_create_priority(spn_stream_t* stream, int high);
 int spn_stream_destroy(spn_stream_t stream);
 int spn_stream_sync(spn_stream_t stream);         /* device.finish() = cuStreamSynchronize(current), occa/src/core/device.cpp:250-254 */
 int spn_malloc(void** dptr, size_t bytes);        /* cuMemAlloc, uninitialised: occa/.../cuda/buffer.cpp:65-67 */
@@ -216,6 +219,47 @@ int spn_ogs_halo_gather_pack(int Nrows, int Nsend, int K, const int* rowStarts, 
 int spn_ogs_halo_combine_scatter(int Nrows, int NrowsP, int K, const int* cmbStarts, const int* cmbIds,
                                  const void* ownBuf, const void* recvBuf, const int* sRowStarts, const int* sColIds,
                                  void* out, int type, int op, spn_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Peer-memory halo exchange over NVLink (one process per GPU, buffers shared with CUDA IPC).
+ * Instead of packing into a local send buffer and handing it to MPI / NCCL
+ * (libs/ogs/ogsPairwise.cpp:115-152), the pack kernel stores every send slot STRAIGHT INTO THE
+ * DESTINATION RANK'S RECEIVE BUFFER (P2P stores through NVSwitch) and, when the whole launch has
+ * stored, raises a flag word in each destination (release at system scope).  The combine kernel of
+ * the destination acquires the flags of its sources before it reads the receive buffer.  No
+ * communication kernel, no SM taken from the interior operator, no host synchronisation.
+ *   send side: slots [slot0[i], slot0[i+1]) go to destination i, slot slot0[i] landing at dst[i];
+ *              flag[i] (in destination i's memory) is set to `epoch` once every slot is stored.
+ *   wait side: flag[i] are LOCAL words written by source i; the kernel waits until each is >= epoch.
+ * `counter` is a zero-initialised local device word used to detect the last block (self-resetting).
+ * ---------------------------------------------------------------------- */
+#define SPN_P2P_MAX_PEERS 32
+#define SPN_IPC_HANDLE_BYTES 64
+typedef struct {
+  int npeers;
+  int slot0[SPN_P2P_MAX_PEERS + 1];
+  void* dst[SPN_P2P_MAX_PEERS];
+  unsigned long long* flag[SPN_P2P_MAX_PEERS];
+  unsigned long long epoch;
+  unsigned int* counter;
+} spn_p2p_send_t;
+typedef struct {
+  int nsrc;
+  const unsigned long long* flag[SPN_P2P_MAX_PEERS];
+  unsigned long long epoch;
+} spn_p2p_wait_t;
+int spn_ipc_get_handle(void* dptr, void* handle64);            /* cudaIpcGetMemHandle of a spn_malloc block   */
+int spn_ipc_open_handle(const void* handle64, void** dptr);    /* map a peer's block (enables peer access)    */
+int spn_ipc_close_handle(void* dptr);
+/* spn_ogs_halo_gather_pack with the send slots stored into the destinations (sendBuf is not used) */
+int spn_ogs_halo_gather_pack_p2p(int Nrows, int Nsend, int K, const int* rowStarts, const int* colIds, const int* sendIds,
+                                 const void* v, void* ownBuf, const spn_p2p_send_t* send, int type, int op, spn_stream_t stream);
+/* spn_ogs_extract with the output stored into the destinations (Scatter NoTrans: owners send their rows) */
+int spn_ogs_extract_p2p(int N, int K, const int* ids, const void* q, const spn_p2p_send_t* send, int type, spn_stream_t stream);
+/* spn_ogs_halo_combine_scatter that first waits for the sources' flags */
+int spn_ogs_halo_combine_scatter_p2p(int Nrows, int NrowsP, int K, const int* cmbStarts, const int* cmbIds,
+                                     const void* ownBuf, const void* recvBuf, const spn_p2p_wait_t* wait,
+                                     const int* sRowStarts, const int* sColIds, void* out, int type, int op, spn_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Device-buffer communication over NCCL — replaces comm_t::{Isend,Irecv,

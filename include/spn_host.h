@@ -53,7 +53,7 @@ int spn_host_ogs_setup(spn_host_ogs_t* ogs, int N, long long* ids, spn_host_comm
                        int verbose, spn_host_platform_t platform);
 int spn_host_ogs_free(spn_host_ogs_t ogs);
 /* info[16]: N, Ngather, NgatherGlobal, NlocalT, NlocalP, NhaloT, NhaloP, gather_defined, local nnzT, local nnzN,
- *           halo nnzT, halo nnzN, local tiles, 0, 0, 0 */
+ *           halo nnzT, halo nnzN, local tiles, peer_exchange (1: halo data moves by P2P stores, 0: NCCL send/recv), 0, 0 */
 int spn_host_ogs_info(spn_host_ogs_t ogs, long long* info);
 /* exchange mode info[8]: Nsend, Nrecv, NrowsP, Nrows, NranksSend, NranksRecv, 0, 0   (mode: 0 Sym 1 NoTrans 2 Trans) */
 int spn_host_ogs_exchange_info(spn_host_ogs_t ogs, int mode, long long* info);
@@ -77,6 +77,9 @@ int spn_host_ogs_gather_scatter_host_start(spn_host_ogs_t ogs, void* h_v, int k,
 int spn_host_ogs_gather_scatter_host_finish(spn_host_ogs_t ogs, void* h_v);
 int spn_host_ogs_gather(spn_host_ogs_t ogs, void* d_gv, const void* d_v, int k, int type, int op, int trans);
 int spn_host_ogs_scatter(spn_host_ogs_t ogs, void* d_v, const void* d_gv, int k, int type, int trans);
+
+/* timing probes (key 0: bit mask of ogs_t::GatherScatter phases to skip); not part of the drop-in surface */
+int spn_host_debug_set(int key, int value);
 
 #ifdef __cplusplus
 }

@@ -167,6 +167,9 @@ void pack_rows_into_lines(const std::vector<int>& rows, const int* rs, const int
 // (ogs_tile.cuh) even when the plan has class tiles; 2 class tiles without the register pipeline
 int g_variant = 0;
 int g_probe = 0;
+// iterations a warp of the gather / gather+scatter tile kernel runs before its CTA retires (spn_debug_set key 4);
+// 0 = persistent grid.  Short-lived CTAs let the halo kernels of a partitioned mesh (higher-priority stream) in.
+int g_chunk_iters = 16;
 
 template <typename K>
 int resident_ctas(K kern, int threads, int* cache) {
@@ -257,7 +260,11 @@ int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaSt
       static int res = 0;
       rc = resident_ctas(kern, TH, &res);
       if (rc) return rc;
-      kern<<<std::min(ctas_needed, res * d->sms), TH, 0, st>>>(NT, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+      const int chunk = g_chunk_iters > 0 ? g_chunk_iters * (TH / 32) * U : 0;
+      if (chunk > 0 && ctas_needed > res * d->sms)
+        kern<<<(NT + chunk - 1) / chunk, TH, 0, st>>>(NT, chunk, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+      else
+        kern<<<std::min(ctas_needed, res * d->sms), TH, 0, st>>>(NT, 0, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
     } else if (K == 1) {
       auto kern = ogs_tile_kernel<T, OP, MODE, U, true, TH, MB>;
       static int res = 0;
@@ -491,6 +498,7 @@ int spn_debug_set(int key, int value) {
   if (key == 1) { g_probe = value; return SPN_SUCCESS; }
   if (key == 2 && value >= 32) { g_slice_rows = value; return SPN_SUCCESS; }
   if (key == 3) { g_class_tiles = value; return SPN_SUCCESS; }
+  if (key == 4 && value >= 0) { g_chunk_iters = value; return SPN_SUCCESS; }
   return SPN_ERR_INVALID_ARGUMENT;
 }
 

@@ -246,16 +246,29 @@ ogs_tile_kernel(int NT, int K, const unsigned* __restrict__ colP, const int* __r
 // ---------------------------------------------------------------------------
 template <typename T, int OP, int MODE, int U, int THREADS, int MINB, int VAR = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
-ogs_tile_pf_kernel(int NT, const unsigned* __restrict__ colP, const int* __restrict__ row0, const T* in, T* out) {
+ogs_tile_pf_kernel(int NTall, int chunkTiles, const unsigned* __restrict__ colP, const int* __restrict__ row0, const T* in, T* out) {
   static_assert(MODE == TILE_GATHER || MODE == TILE_GATHER_SCATTER, "scatter runs by columns");
   static_assert(U <= kTilePad, "tile padding too small");
   const int lane = threadIdx.x & 31;
-  const int warp = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 5);
-  const int nwarps = (int)((gridDim.x * (unsigned)THREADS) >> 5);
   const unsigned le_mask = 0xffffffffu >> (31 - lane);
-  const int64_t step = (int64_t)nwarps * U;
-
-  int64_t base = (int64_t)warp * U;
+  // Work split.  chunkTiles == 0: persistent grid, warp w of the whole grid walks tiles w*U, w*U + step, ...
+  // chunkTiles  > 0: CTA b owns the contiguous tiles [b*chunk, (b+1)*chunk) and retires after them, so that
+  // concurrently resident CTAs sweep one contiguous window of the mesh and a higher-priority stream (the halo
+  // kernels of a partitioned mesh) finds free SM slots every few microseconds.
+  int64_t base, step;
+  int NT;
+  if (chunkTiles > 0) {
+    const int64_t c0 = (int64_t)blockIdx.x * chunkTiles;
+    base = c0 + (int64_t)(threadIdx.x >> 5) * U;
+    step = (int64_t)(THREADS / 32) * U;
+    NT = (int)min((int64_t)NTall, c0 + chunkTiles);
+  } else {
+    const int warp = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 5);
+    const int nwarps = (int)((gridDim.x * (unsigned)THREADS) >> 5);
+    base = (int64_t)warp * U;
+    step = (int64_t)nwarps * U;
+    NT = NTall;
+  }
   if (base >= NT) return;
 
   unsigned wc[U], w1[U];

@@ -170,4 +170,36 @@ int spn_event_elapsed_ms(spn_event_t start, spn_event_t stop, float* ms) {
   return SPN_SUCCESS;
 }
 
+int spn_stream_create_priority(spn_stream_t* stream, int high) {
+  if (!stream) return SPN_ERR_INVALID_ARGUMENT;
+  int lo = 0, hi = 0;
+  SPN_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // numerically lower = higher priority
+  cudaStream_t s;
+  SPN_CUDA_TRY(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high ? hi : lo));
+  *stream = reinterpret_cast<spn_stream_t>(s);
+  return SPN_SUCCESS;
+}
+
+// ---- CUDA IPC: share a spn_malloc block with the other ranks of the node (peer-memory halo exchange) ----
+int spn_ipc_get_handle(void* dptr, void* handle64) {
+  if (!dptr || !handle64) return SPN_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == SPN_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  cudaIpcMemHandle_t h;
+  SPN_CUDA_TRY(cudaIpcGetMemHandle(&h, dptr));
+  memcpy(handle64, &h, sizeof(h));
+  return SPN_SUCCESS;
+}
+int spn_ipc_open_handle(const void* handle64, void** dptr) {
+  if (!dptr || !handle64) return SPN_ERR_INVALID_ARGUMENT;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  SPN_CUDA_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SPN_SUCCESS;
+}
+int spn_ipc_close_handle(void* dptr) {
+  if (!dptr) return SPN_SUCCESS;
+  SPN_CUDA_TRY(cudaIpcCloseMemHandle(dptr));
+  return SPN_SUCCESS;
+}
+
 }  // extern "C"

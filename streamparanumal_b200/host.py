@@ -45,6 +45,7 @@ _HOST_SIGNATURES = {
     "spn_host_ogs_gather_scatter_finish": [c_void_p, c_void_p, c_int, c_int, c_int, c_int],
     "spn_host_ogs_gather_scatter_host_start": [c_void_p, c_void_p, c_int, c_int, c_int, c_int],
     "spn_host_ogs_gather_scatter_host_finish": [c_void_p, c_void_p],
+    "spn_host_debug_set": [c_int, c_int],
     "spn_host_ogs_gather": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int],
     "spn_host_ogs_scatter": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int],
 }
@@ -164,6 +165,7 @@ class Ogs:
         (self.N, self.Ngather, self.NgatherGlobal, self.NlocalT, self.NlocalP, self.NhaloT, self.NhaloP) = list(info)[:7]
         self.gather_defined = bool(info[7])
         self.local_nnzT, self.local_nnzN, self.halo_nnzT, self.halo_nnzN, self.local_tiles = list(info)[8:13]
+        self.peer_exchange = bool(list(info)[13])
 
     def exchange_info(self, mode):
         info = (c_longlong * 8)()

@@ -7,6 +7,7 @@
 #include "spn_host.h"
 
 using namespace spn;
+namespace spn { namespace ogs { extern int g_debug_skip; } }
 
 struct spn_host_comm { comm_t comm; };
 struct spn_host_platform { platform_t platform; };
@@ -111,6 +112,7 @@ int spn_host_ogs_info(spn_host_ogs_t h, long long* info) {
     spn_ogs_plan_info(o.gatherLocal->planT, &nt, nullptr, nullptr);
     info[12] = nt;
   }
+  info[13] = o.peer_exchange() ? 1 : 0;
   return SPN_SUCCESS;
 }
 int spn_host_ogs_exchange_info(spn_host_ogs_t h, int mode, long long* info) {
@@ -185,6 +187,10 @@ int spn_host_ogs_gather_scatter_host_start(spn_host_ogs_t h, void* h_v, int k, i
 int spn_host_ogs_gather_scatter_host_finish(spn_host_ogs_t h, void* h_v) {
   if (!h) return SPN_ERR_INVALID_ARGUMENT;
   return guarded([&] { h->ogs.HostGatherScatterFinish(h_v); });
+}
+int spn_host_debug_set(int key, int value) {
+  if (key == 0) { spn::ogs::g_debug_skip = value; return SPN_SUCCESS; }
+  return SPN_ERR_INVALID_ARGUMENT;
 }
 int spn_host_ogs_gather(spn_host_ogs_t h, void* gv, const void* v, int k, int type, int op, int trans) {
   if (!h) return SPN_ERR_INVALID_ARGUMENT;

@@ -107,6 +107,7 @@ class ogs_t {
   bool unique = false;
   bool gather_defined = false;
   bool on_device = false;
+  bool peer_exchange() const { return p2p.enabled; }  // true: halo data moves by P2P stores over NVLink, false: NCCL
 
   std::shared_ptr<ogsOperator_t> gatherLocal, gatherHalo;
   ogsExchangeData_t data[3];  // indexed by Transpose
@@ -184,10 +185,43 @@ class ogs_t {
   void StartExchange(const ogsExchangeData_t& d, int k, Type type);   // pack done on the current stream -> NCCL on commStream
   void FinishExchange();                                              // current stream waits for the receive
 
+  // halo rows and interior rows own disjoint columns, so the halo chain (pack -> exchange -> combine) runs on its own
+  // high-priority stream next to the interior operator: ForkHalo makes it wait for everything queued on the current
+  // stream so far, JoinHalo makes the current stream wait for it.
+  spn_stream_t ForkHalo();
+  void JoinHalo();
+  spn_stream_t haloStream = nullptr;
+  spn_event_t forkEvent = nullptr, joinEvent = nullptr;
+  bool halo_forked = false;
+
   deviceMemory<char> o_ownBuf, o_sendBuf, o_recvBuf;
   spn_stream_t commStream = nullptr;
   spn_event_t packedEvent = nullptr, recvEvent = nullptr;
   bool exchange_in_flight = false;
+
+  // peer-memory exchange (include/spn_b200.h "Peer-memory halo exchange"; csrc/ogs_halo.cu): every rank owns one
+  // IPC-shared block  [flags: one word per source rank | receive half 0 | receive half 1].  The pack kernel of a
+  // call stores its send slots into half (epoch & 1) of each destination and sets flags[me] = epoch there; the
+  // combine kernel waits for flags[src] >= epoch.  Two halves are enough: a rank cannot start call n+2 before its
+  // neighbours finished reading call n (its combine of n+1 waits for their pack of n+1, which follows their
+  // combine of n in stream order).  Used when an entry is <= 8 bytes (K*sizeof(T)); otherwise, or when IPC is not
+  // available or SPN_OGS_EXCHANGE=nccl, the NCCL send/recv path runs.
+  struct PeerExchange {
+    bool enabled = false;
+    deviceMemory<char> o_block;
+    deviceMemory<unsigned int> o_counter;
+    size_t flagBytes = 0, halfBytes = 0;
+    std::vector<void*> peerBlock;        // [size]: mapped block of every neighbour, nullptr otherwise
+    std::vector<dlong> remoteOffset[3];  // [mode][i]: slot of my first entry in the receive buffer of sendRanks[i]
+    unsigned long long epoch = 0;
+  };
+  PeerExchange p2p;
+  void SetupPeerExchange();
+  void FreePeerExchange();
+  bool UsePeerExchange(size_t Nbytes) const { return p2p.enabled && Nbytes <= sizeof(dfloat); }
+  void PeerSendTable(spn_p2p_send_t& s, int mode, size_t Nbytes);      // starts a new epoch
+  const void* PeerWaitTable(spn_p2p_wait_t& w, int mode) const;        // returns the receive half of the current epoch
+  bool peer_exchange_in_flight = false;
 
   // staging of the host-buffer operations
   struct HostStage {

@@ -17,6 +17,10 @@
 namespace spn {
 namespace ogs {
 
+// timing probe (spn_host_debug_set(0, mask)): 1 skip the halo pack / send, 2 skip the interior operator,
+// 4 skip the halo combine.  Results are wrong with any bit set; used by tools/halo_breakdown.py only.
+int g_debug_skip = 0;
+
 // ---------------------------------------------------------------------------------------------
 // ogsOperator_t
 // ---------------------------------------------------------------------------------------------
@@ -130,10 +134,27 @@ void ogs_t::AllocBuffer(size_t Nbytes) {
   if (o_recvBuf.size() < (size_t)d.Nrecv * Nbytes) o_recvBuf = platform.malloc<char>((size_t)d.Nrecv * Nbytes);
 }
 
+spn_stream_t ogs_t::ForkHalo() {
+  if (!haloStream) return platform.getStream();  // one rank: no separate halo chain
+  if (!halo_forked) {
+    SPN_CHECK(spn_event_record(forkEvent, platform.getStream()));
+    SPN_CHECK(spn_stream_wait_event(haloStream, forkEvent));
+    halo_forked = true;
+  }
+  return haloStream;
+}
+
+void ogs_t::JoinHalo() {
+  if (!halo_forked) return;
+  SPN_CHECK(spn_event_record(joinEvent, haloStream));
+  SPN_CHECK(spn_stream_wait_event(platform.getStream(), joinEvent));
+  halo_forked = false;
+}
+
 void ogs_t::StartExchange(const ogsExchangeData_t& d, int k, Type type) {
   if (comm.size() == 1) return;
   const size_t Nbytes = Sizeof(type) * (size_t)k;
-  spn_stream_t cur = platform.getStream();
+  spn_stream_t cur = ForkHalo();  // the pack ran there
   SPN_CHECK(spn_event_record(packedEvent, cur));
   SPN_CHECK(spn_stream_wait_event(commStream, packedEvent));
   const int nr = (int)d.recvRanks.size(), ns = (int)d.sendRanks.size();
@@ -148,7 +169,7 @@ void ogs_t::StartExchange(const ogsExchangeData_t& d, int k, Type type) {
 
 void ogs_t::FinishExchange() {
   if (!exchange_in_flight) return;
-  SPN_CHECK(spn_stream_wait_event(platform.getStream(), recvEvent));
+  SPN_CHECK(spn_stream_wait_event(ForkHalo(), recvEvent));  // the combine runs there
   exchange_in_flight = false;
 }
 
@@ -158,28 +179,52 @@ void ogs_t::FinishExchange() {
 void ogs_t::GatherScatterStart(void* o_v, int k, Type type, Op op, Transpose trans) {
   SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
   if (NhaloT == 0 && comm.size() == 1) return;
+  if (g_debug_skip & 1) return;
   AllocBuffer((size_t)k * Sizeof(type));
   const ogsExchangeData_t& d = data[trans];
   // halo partials: gather over the T copies unless NoTrans (positive copies only), straight into send order
   const bool useN = (trans == NoTrans);
-  SPN_CHECK(spn_ogs_halo_gather_pack(NhaloT, d.Nsend, k, useN ? gatherHalo->o_rowStartsN.ptr() : gatherHalo->o_rowStartsT.ptr(),
-                                     useN ? gatherHalo->o_colIdsN.ptr() : gatherHalo->o_colIdsT.ptr(), d.o_sendIds.ptr(), o_v,
-                                     o_ownBuf.ptr(), o_sendBuf.ptr(), type, op, platform.getStream()));
+  const dlong* hRS = useN ? gatherHalo->o_rowStartsN.ptr() : gatherHalo->o_rowStartsT.ptr();
+  const dlong* hCI = useN ? gatherHalo->o_colIdsN.ptr() : gatherHalo->o_colIdsT.ptr();
+  if (comm.size() > 1 && UsePeerExchange((size_t)k * Sizeof(type))) {
+    // partials go straight into the neighbours' receive buffers (P2P stores), flags raised by the same launch
+    spn_p2p_send_t send;
+    PeerSendTable(send, trans, (size_t)k * Sizeof(type));
+    SPN_CHECK(spn_ogs_halo_gather_pack_p2p(NhaloT, d.Nsend, k, hRS, hCI, d.o_sendIds.ptr(), o_v, o_ownBuf.ptr(), &send, type, op,
+                                           ForkHalo()));
+    peer_exchange_in_flight = true;
+    return;
+  }
+  SPN_CHECK(spn_ogs_halo_gather_pack(NhaloT, d.Nsend, k, hRS, hCI, d.o_sendIds.ptr(), o_v, o_ownBuf.ptr(), o_sendBuf.ptr(), type,
+                                     op, ForkHalo()));
   StartExchange(d, k, type);
 }
 
 void ogs_t::GatherScatterFinish(void* o_v, int k, Type type, Op op, Transpose trans) {
   SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
   spn_stream_t cur = platform.getStream();
-  gatherLocal->GatherScatter(o_v, k, type, op, trans, cur);  // interior rows, overlaps the exchange
+  spn_stream_t hs = (NhaloT == 0 && comm.size() == 1) ? cur : ForkHalo();  // halo chain: its own stream, next to the interior operator
+  if (!(g_debug_skip & 2)) gatherLocal->GatherScatter(o_v, k, type, op, trans, cur);  // interior rows
   if (NhaloT == 0 && comm.size() == 1) return;
-  FinishExchange();
+  if (g_debug_skip & 4) { peer_exchange_in_flight = false; FinishExchange(); JoinHalo(); return; }
   const ogsExchangeData_t& d = data[trans];
   // scatter side: every copy, except Trans which writes positive copies only (ogsOperator.cpp:303-321)
   const bool sN = (trans == Trans);
+  const dlong* sRS = sN ? gatherHalo->o_rowStartsN.ptr() : gatherHalo->o_rowStartsT.ptr();
+  const dlong* sCI = sN ? gatherHalo->o_colIdsN.ptr() : gatherHalo->o_colIdsT.ptr();
+  if (peer_exchange_in_flight) {
+    spn_p2p_wait_t wait;
+    const void* recv = PeerWaitTable(wait, trans);
+    SPN_CHECK(spn_ogs_halo_combine_scatter_p2p(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), o_ownBuf.ptr(), recv,
+                                               &wait, sRS, sCI, o_v, type, op, hs));
+    peer_exchange_in_flight = false;
+    JoinHalo();
+    return;
+  }
+  FinishExchange();
   SPN_CHECK(spn_ogs_halo_combine_scatter(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), o_ownBuf.ptr(),
-                                         o_recvBuf.ptr(), sN ? gatherHalo->o_rowStartsN.ptr() : gatherHalo->o_rowStartsT.ptr(),
-                                         sN ? gatherHalo->o_colIdsN.ptr() : gatherHalo->o_colIdsT.ptr(), o_v, type, op, cur));
+                                         o_recvBuf.ptr(), sRS, sCI, o_v, type, op, hs));
+  JoinHalo();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -239,11 +284,19 @@ void ogs_t::GatherStart(void* o_gv, const void* o_v, int k, Type type, Op op, Tr
   if (trans == Trans) {  // partials travel to the positive copy
     AllocBuffer(Nbytes);
     const ogsExchangeData_t& d = data[Trans];
+    if (comm.size() > 1 && UsePeerExchange(Nbytes)) {
+      spn_p2p_send_t send;
+      PeerSendTable(send, Trans, Nbytes);
+      SPN_CHECK(spn_ogs_halo_gather_pack_p2p(NhaloT, d.Nsend, k, gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(),
+                                             d.o_sendIds.ptr(), o_v, o_ownBuf.ptr(), &send, type, op, ForkHalo()));
+      peer_exchange_in_flight = true;
+      return;
+    }
     SPN_CHECK(spn_ogs_halo_gather_pack(NhaloT, d.Nsend, k, gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(),
-                                       d.o_sendIds.ptr(), o_v, o_ownBuf.ptr(), o_sendBuf.ptr(), type, op, platform.getStream()));
+                                       d.o_sendIds.ptr(), o_v, o_ownBuf.ptr(), o_sendBuf.ptr(), type, op, ForkHalo()));
     StartExchange(d, k, type);
   } else {  // no communication: gather the halo rows in place behind the local rows
-    gatherHalo->Gather(static_cast<char*>(o_gv) + Nbytes * (size_t)NlocalT, o_v, k, type, op, trans, platform.getStream());
+    gatherHalo->Gather(static_cast<char*>(o_gv) + Nbytes * (size_t)NlocalT, o_v, k, type, op, trans, ForkHalo());
   }
 }
 
@@ -251,15 +304,28 @@ void ogs_t::GatherFinish(void* o_gv, const void* o_v, int k, Type type, Op op, T
   SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
   AssertGatherDefined();
   spn_stream_t cur = platform.getStream();
+  spn_stream_t hs = (NhaloT > 0) ? ForkHalo() : cur;
   gatherLocal->Gather(o_gv, o_v, k, type, op, trans, cur);
+  if (trans != Trans || NhaloT == 0) JoinHalo();
   if (trans == Trans && NhaloT > 0) {
-    FinishExchange();
     const ogsExchangeData_t& d = data[Trans];
     const size_t Nbytes = (size_t)k * Sizeof(type);
+    if (peer_exchange_in_flight) {
+      spn_p2p_wait_t wait;
+      const void* recv = PeerWaitTable(wait, Trans);
+      SPN_CHECK(spn_ogs_halo_combine_scatter_p2p(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), o_ownBuf.ptr(), recv,
+                                                 &wait, nullptr, nullptr, static_cast<char*>(o_gv) + Nbytes * (size_t)NlocalT,
+                                                 type, op, hs));
+      peer_exchange_in_flight = false;
+      JoinHalo();
+      return;
+    }
+    FinishExchange();
     // fold straight into the tail of o_gv (the reference folds into o_recvBuf and copies: ogs.cpp:270-277)
     SPN_CHECK(spn_ogs_halo_combine_scatter(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), o_ownBuf.ptr(),
                                            o_recvBuf.ptr(), nullptr, nullptr,
-                                           static_cast<char*>(o_gv) + Nbytes * (size_t)NlocalT, type, op, cur));
+                                           static_cast<char*>(o_gv) + Nbytes * (size_t)NlocalT, type, op, hs));
+    JoinHalo();
   }
 }
 
@@ -274,8 +340,16 @@ void ogs_t::ScatterStart(void* /*o_v*/, const void* o_gv, int k, Type type, Tran
   AllocBuffer(Nbytes);
   const ogsExchangeData_t& d = data[NoTrans];
   // owners pack their rows of o_gv straight into send order (the reference copies, then extracts: ogs.cpp:423-431)
+  if (comm.size() > 1 && UsePeerExchange(Nbytes)) {
+    spn_p2p_send_t send;
+    PeerSendTable(send, NoTrans, Nbytes);
+    SPN_CHECK(spn_ogs_extract_p2p(d.Nsend, k, d.o_sendIds.ptr(), static_cast<const char*>(o_gv) + Nbytes * (size_t)NlocalT, &send,
+                                  type, ForkHalo()));
+    peer_exchange_in_flight = true;
+    return;
+  }
   SPN_CHECK(spn_ogs_extract(d.Nsend, k, d.o_sendIds.ptr(), static_cast<const char*>(o_gv) + Nbytes * (size_t)NlocalT,
-                            o_sendBuf.ptr(), type, platform.getStream()));
+                            o_sendBuf.ptr(), type, ForkHalo()));
   StartExchange(d, k, type);
 }
 
@@ -283,19 +357,30 @@ void ogs_t::ScatterFinish(void* o_v, const void* o_gv, int k, Type type, Transpo
   SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
   AssertGatherDefined();
   spn_stream_t cur = platform.getStream();
+  spn_stream_t hs = (NhaloT > 0) ? ForkHalo() : cur;
   gatherLocal->Scatter(o_v, o_gv, k, type, trans, cur);
   if (NhaloT == 0) return;
   const size_t Nbytes = (size_t)k * Sizeof(type);
   const char* gvHalo = static_cast<const char*>(o_gv) + Nbytes * (size_t)NlocalT;
   if (trans == NoTrans) {
-    FinishExchange();
     const ogsExchangeData_t& d = data[NoTrans];
+    if (peer_exchange_in_flight) {
+      spn_p2p_wait_t wait;
+      const void* recv = PeerWaitTable(wait, NoTrans);
+      SPN_CHECK(spn_ogs_halo_combine_scatter_p2p(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), gvHalo, recv, &wait,
+                                                 gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(), o_v, type, Add, hs));
+      peer_exchange_in_flight = false;
+      JoinHalo();
+      return;
+    }
+    FinishExchange();
     // rows < NhaloP take their own value from o_gv, the others the owner's (identity (+) x, as postmpi.Gather does)
     SPN_CHECK(spn_ogs_halo_combine_scatter(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), gvHalo, o_recvBuf.ptr(),
-                                           gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(), o_v, type, Add, cur));
+                                           gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(), o_v, type, Add, hs));
   } else {
-    gatherHalo->Scatter(o_v, gvHalo, k, type, trans, cur);
+    gatherHalo->Scatter(o_v, gvHalo, k, type, trans, hs);
   }
+  JoinHalo();
 }
 
 }  // namespace ogs

@@ -15,6 +15,9 @@
 #include <numeric>
 #include <parallel/algorithm>
 
+#include <cstdlib>
+#include <string>
+
 #include "ogs.hpp"
 
 namespace spn {
@@ -142,6 +145,11 @@ void ogs_t::Free() {
   if (packedEvent) { spn_event_destroy(packedEvent); packedEvent = nullptr; }
   if (recvEvent) { spn_event_destroy(recvEvent); recvEvent = nullptr; }
   commStream = nullptr;  // owned by the platform
+  haloStream = nullptr;
+  if (forkEvent) { spn_event_destroy(forkEvent); forkEvent = nullptr; }
+  if (joinEvent) { spn_event_destroy(joinEvent); joinEvent = nullptr; }
+  halo_forked = false;
+  FreePeerExchange();
   for (HostStage& st : stage) {
     if (st.busy) spn_event_sync(st.d2hDone);
     if (st.h2dDone) spn_event_destroy(st.h2dDone);
@@ -161,6 +169,114 @@ void ogs_t::Free() {
   NgatherGlobal = 0;
   on_device = false;
   exchange_in_flight = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer-memory exchange: allocate the shared block, swap IPC handles and receive offsets (collective)
+// ---------------------------------------------------------------------------------------------
+void ogs_t::FreePeerExchange() {
+  if (p2p.enabled) {
+    // nobody may unmap or free a block a neighbour can still store into
+    try {
+      platform.finish();
+      comm.Barrier();
+    } catch (...) {
+    }
+  }
+  for (void*& b : p2p.peerBlock)
+    if (b) { spn_ipc_close_handle(b); b = nullptr; }
+  p2p = PeerExchange();
+  peer_exchange_in_flight = false;
+}
+
+void ogs_t::SetupPeerExchange() {
+  const int size = comm.size(), rank = comm.rank();
+  const char* mode_env = getenv("SPN_OGS_EXCHANGE");
+  int want = !(mode_env && std::string(mode_env) == "nccl") && size <= 64 ? 1 : 0;
+  for (int m = 0; m < 3; ++m)
+    if ((int)data[m].sendRanks.size() > SPN_P2P_MAX_PEERS || (int)data[m].recvRanks.size() > SPN_P2P_MAX_PEERS) want = 0;
+  comm.Allreduce(want, Comm::Min);
+  if (!want) return;
+
+  dlong maxRecv = 0;
+  for (int m = 0; m < 3; ++m) maxRecv = std::max(maxRecv, data[m].Nrecv);
+  auto align = [](size_t b) { return (b + 255) / 256 * 256; };
+  p2p.flagBytes = align(sizeof(unsigned long long) * (size_t)size);
+  p2p.halfBytes = align(sizeof(dfloat) * (size_t)std::max<dlong>(maxRecv, 1));
+  const size_t blockBytes = p2p.flagBytes + 2 * p2p.halfBytes;
+  p2p.o_block = platform.malloc<char>(blockBytes);
+  p2p.o_counter = platform.malloc<unsigned int>(1);
+  SPN_CHECK(spn_memset(p2p.o_block.ptr(), 0, blockBytes, platform.getStream()));
+  SPN_CHECK(spn_memset(p2p.o_counter.ptr(), 0, sizeof(unsigned int), platform.getStream()));
+  platform.finish();
+
+  // handles of every rank's block
+  std::vector<char> mine(SPN_IPC_HANDLE_BYTES, 0), all((size_t)SPN_IPC_HANDLE_BYTES * size, 0);
+  int ok = spn_ipc_get_handle(p2p.o_block.ptr(), mine.data()) == SPN_SUCCESS ? 1 : 0;
+  comm.Allgather(mine.data(), all.data(), SPN_IPC_HANDLE_BYTES);
+  comm.Allreduce(ok, Comm::Min);
+
+  // neighbours in any mode
+  std::vector<char> isNbr((size_t)size, 0);
+  for (int m = 0; m < 3; ++m) {
+    for (int r : data[m].sendRanks) isNbr[r] = 1;
+    for (int r : data[m].recvRanks) isNbr[r] = 1;
+  }
+  p2p.peerBlock.assign((size_t)size, nullptr);
+  if (ok) {
+    for (int r = 0; r < size && ok; ++r) {
+      if (!isNbr[r] || r == rank) continue;
+      void* mapped = nullptr;
+      if (spn_ipc_open_handle(all.data() + (size_t)SPN_IPC_HANDLE_BYTES * r, &mapped) != SPN_SUCCESS) ok = 0;
+      else p2p.peerBlock[r] = mapped;
+    }
+  }
+  comm.Allreduce(ok, Comm::Min);
+
+  // where my entries land in each destination: the destination's recvOffsets entry for me, per mode
+  for (int m = 0; m < 3; ++m) {
+    std::vector<dlong> tell((size_t)size, -1), got((size_t)size, -1);
+    for (size_t i = 0; i < data[m].recvRanks.size(); ++i) tell[data[m].recvRanks[i]] = data[m].recvOffsets[i];
+    comm.Alltoall(tell.data(), got.data());
+    p2p.remoteOffset[m].assign(data[m].sendRanks.size(), 0);
+    for (size_t i = 0; i < data[m].sendRanks.size(); ++i) {
+      const dlong off = got[data[m].sendRanks[i]];
+      if (off < 0) ok = 0;  // the destination does not expect me: plans disagree
+      p2p.remoteOffset[m][i] = off;
+    }
+  }
+  comm.Allreduce(ok, Comm::Min);
+  if (!ok) {
+    if (rank == 0) fprintf(stderr, "spn ogs: CUDA IPC peer access unavailable, halo exchange stays on NCCL send/recv\n");
+    FreePeerExchange();
+    return;
+  }
+  p2p.enabled = true;
+}
+
+void ogs_t::PeerSendTable(spn_p2p_send_t& s, int mode, size_t Nbytes) {
+  const ogsExchangeData_t& d = data[mode];
+  const unsigned long long epoch = ++p2p.epoch;
+  const size_t half = p2p.flagBytes + (size_t)(epoch & 1ull) * p2p.halfBytes;
+  s.npeers = (int)d.sendRanks.size();
+  for (int i = 0; i < s.npeers; ++i) {
+    char* block = static_cast<char*>(p2p.peerBlock[d.sendRanks[i]]);
+    s.slot0[i] = d.sendOffsets[i];
+    s.dst[i] = block + half + (size_t)p2p.remoteOffset[mode][i] * Nbytes;
+    s.flag[i] = reinterpret_cast<unsigned long long*>(block) + comm.rank();
+  }
+  s.slot0[s.npeers] = d.Nsend;
+  s.epoch = epoch;
+  s.counter = p2p.o_counter.ptr();
+}
+
+const void* ogs_t::PeerWaitTable(spn_p2p_wait_t& w, int mode) const {
+  const ogsExchangeData_t& d = data[mode];
+  w.nsrc = (int)d.recvRanks.size();
+  for (int i = 0; i < w.nsrc; ++i)
+    w.flag[i] = reinterpret_cast<const unsigned long long*>(p2p.o_block.ptr()) + d.recvRanks[i];
+  w.epoch = p2p.epoch;
+  return p2p.o_block.ptr() + p2p.flagBytes + (size_t)(p2p.epoch & 1ull) * p2p.halfBytes;
 }
 
 void ogs_t::AssertGatherDefined() const {
@@ -196,9 +312,13 @@ void ogs_t::Setup(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_, co
   }
   if (comm.size() > 1) {
     commStream = platform.createStream();
+    haloStream = platform.createStream(/*high_priority=*/true);
+    SPN_CHECK(spn_event_create(&forkEvent));
+    SPN_CHECK(spn_event_create(&joinEvent));
     SPN_CHECK(spn_event_create(&packedEvent));
     SPN_CHECK(spn_event_create(&recvEvent));
     comm.device();  // NCCL communicator: collective, every rank reaches this point
+    SetupPeerExchange();
   }
   AllocBuffer(sizeof(dfloat));
   on_device = true;

@@ -23,9 +23,10 @@ int platform_t::smCount() const {
   return sms;
 }
 
-spn_stream_t platform_t::createStream() {
+spn_stream_t platform_t::createStream(bool high_priority) {
   spn_stream_t s = nullptr;
-  SPN_CHECK(spn_stream_create(&s));
+  if (high_priority) SPN_CHECK(spn_stream_create_priority(&s, 1));
+  else SPN_CHECK(spn_stream_create(&s));
   state_->owned.push_back(s);
   return s;
 }

@@ -157,7 +157,7 @@ class platform_t {
   // kernels and async copies go to it (occa/src/occa/internal/modes/cuda/kernel.cpp:96-100)
   spn_stream_t getStream() const { return *state_->current; }
   void setStream(spn_stream_t s) { *state_->current = s; }
-  spn_stream_t createStream();
+  spn_stream_t createStream(bool high_priority = false);
   void finish() { SPN_CHECK(spn_stream_sync(*state_->current)); }  // device.finish()
   const std::shared_ptr<spn_stream_t>& streamSlot() const { return state_->current; }
 

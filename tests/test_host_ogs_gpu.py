@@ -5,8 +5,8 @@ reference-facing API of this path (include/ogs.hpp:216-341) driven exactly as BS
   * one rank: Gather / Scatter / GatherScatter (+ Start/Finish halves) on the device against the
     oracle walking the same host plan (tests/ogs_sim.py), every Transpose mode, K in {1,3},
     all four element types, masked (id 0) nodes;
-  * 2/4/8 ranks, one GPU each (skipped when the box has fewer GPUs): the NCCL pairwise exchange +
-    fused halo kernels against the same walk with a gloo exchange — bit-exact, because the fold
+  * 2/4/8 ranks, one GPU each (skipped when the box has fewer GPUs): the pairwise exchange — peer-memory
+    stores over NVLink ("p2p", the default) and NCCL send/recv ("nccl") — + fused halo kernels against the same walk with a gloo exchange — bit-exact, because the fold
     order (own partial, then ascending source rank: libs/ogs/ogsPairwise.cpp:214-232) is kept —
     and the scalar NCCL allreduce behind norm/dot/rdotr at P>1.
 """
@@ -161,12 +161,13 @@ def test_single_rank_bs8_config_shape():
 
 
 # ---- multi-rank -----------------------------------------------------------------------------------
-def _worker(rank, world, port, tmpdir, nx, ny, nz, p, K, dtype_name, kind_unique):
+def _worker(rank, world, port, tmpdir, nx, ny, nz, p, K, dtype_name, kind_unique, exchange):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["LOCAL_RANK"] = str(rank)
+    os.environ["SPN_OGS_EXCHANGE"] = exchange
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -180,6 +181,10 @@ def _worker(rank, world, port, tmpdir, nx, ny, nz, p, K, dtype_name, kind_unique
         kind, unique = kind_unique
         ogs = host.Ogs(ids, comm, kind=kind, unique=unique, platform=platform)
         assert ogs.NhaloT > 0
+        if exchange == "nccl":
+            assert not ogs.peer_exchange
+        elif not ogs.peer_exchange and rank == 0:
+            print("WARNING: CUDA IPC peer access unavailable on this box: the p2p case ran over NCCL", flush=True)
         if kind == host.SIGNED:
             assert comm.allreduce(int(ogs.Ngather)) == nglobal == ogs.NgatherGlobal
         plan = ogs_sim.Plan(ogs)
@@ -228,10 +233,11 @@ MULTI = [
 ]
 
 
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("world,nx,ny,nz,p,K,dtype,kind_unique", MULTI)
-def test_multirank_ogs_t_nccl(world, nx, ny, nz, p, K, dtype, kind_unique):
+def test_multirank_ogs_t_nccl(world, nx, ny, nz, p, K, dtype, kind_unique, exchange):
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")
     with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
-        mp.spawn(_worker, args=(world, _free_port(), tmpdir, nx, ny, nz, p, K, dtype, kind_unique), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), tmpdir, nx, ny, nz, p, K, dtype, kind_unique, exchange), nprocs=world, join=True)
