@@ -47,7 +47,7 @@ def bs8_bytes(Nt, Ng):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one BS8 launch at the headline size, from the ncu --set full
 # capture summarised in profiles/ (None until a capture at this size is committed)
-TRAFFIC_BS8 = None
+TRAFFIC_BS8 = 2644430000  # profiles/r01_ncu_full_summary_w.txt: 1.616629 GB read + 1.027801 GB written (64^3, degree 7)
 
 
 def bs6_bytes(Nt, Ng):

@@ -5,7 +5,7 @@
 //
 // What is the same: flags and defaults, N = B / (bytes per entry), 5 warm-up calls at Nmax, 20 timed calls per
 // size between GlobalPlatformTime stamps, bytes counted as the reference counts them, the output format.
-// What differs: kernel1 of BS3-5 finishes the reduction itself (last-block-done), so kernel2 only folds the
+// What differs: with more than one rank the BS3-5 scalar is summed over the ranks by ncclAllReduce on the device; kernel1 of BS3-5 finishes the reduction itself (last-block-done), so kernel2 only folds the
 // Nblock-entry tmp array the reference way; N is kept in 64 bits internally (the reference's `int N` overflows
 // above 2^31 entries, which no BS flag reaches at 4 GiB).
 #include <cstdio>
@@ -141,6 +141,9 @@ void run(platform_t& platform, settings_t& settings) {
     kernel1(Nblock, n, o_a, alpha, o_b, o_tmp);  // o_a = Ap, o_b = r
 #endif
     kernel2(Nblock, o_tmp, o_out);
+    // partitioned run: the scalar is the sum over ranks (north star: NCCL allreduce behind norm / dot / r.r; the
+    // reference drivers leave one partial result per rank)
+    if (platform.size() > 1) platform.comm.AllreduceDevice(o_out.ptr(), 1, platform.getStream());
 #endif
   };
 
