@@ -47,7 +47,7 @@ def bs8_bytes(Nt, Ng):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one BS8 launch at the headline size, from the ncu --set full
 # capture summarised in profiles/ (None until a capture at this size is committed)
-TRAFFIC_BS8 = 2644430000  # profiles/r01_ncu_full_summary_w.txt: 1.616629 GB read + 1.027801 GB written (64^3, degree 7)
+TRAFFIC_BS8 = 2652936000  # profiles/r01_ncu_full_summary_f.txt: 1.619144 GB read + 1.033792 GB written (64^3, degree 7)
 
 
 def bs6_bytes(Nt, Ng):
@@ -383,7 +383,7 @@ def run_b200(args):
                    "l2": "q (1.07 GB) + ids (0.54 GB) per call exceed the 126 MB L2; no flush needed",
                    "host_setup_s": round(t_setup, 2)},
         "effective_gbs": bytes_step / t_step * 1e-9,
-        "roofline": {"bound": "hbm", "kernel": "ogs_tile_pf_kernel<double,Add,GATHER_SCATTER>",
+        "roofline": {"bound": "hbm", "kernel": "ogs_tile_pf_kernel<double,Add,GATHER_SCATTER,U=4,256 threads,4 CTAs/SM>",
                      "achieved": bytes_rank / t_step * 1e-9, "peak": peak, "peak_source": peak_src,
                      "unit": "GB/s", "frac": bytes_rank / t_step * 1e-9 / peak,
                      "frac_of_8TBs_nominal": bytes_rank / t_step * 1e-9 / 8000.0,

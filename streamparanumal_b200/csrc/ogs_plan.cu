@@ -8,7 +8,8 @@
 #include <vector>
 #include "ogs_ctile.cuh"
 
-// Launch geometry per operation, from the sweep in profiles/round1_notes.md (B200, degree-7 hex):
+// Launch geometry per operation, from the sweeps in profiles/r01_notes.md (B200, degree-7 hex; gather+scatter re-swept
+// after the instruction diet of the fold: U=4 with four resident CTAs beats U=8 with two, 0.487 vs 0.517 ms):
 // U = tiles a warp keeps in flight, MINB = resident 256-thread CTAs per SM the register
 // allocator must allow.  -DSPN_TILE_U / -DSPN_TILE_MINB override all three for sweeps.
 #ifndef SPN_TILE_THREADS
@@ -21,7 +22,7 @@
 #else
 #define SPN_TILE_U_G 4
 #define SPN_TILE_U_S 8
-#define SPN_TILE_U_GS 8
+#define SPN_TILE_U_GS 4
 #endif
 #ifdef SPN_TILE_MINB
 #define SPN_TILE_MINB_G SPN_TILE_MINB
@@ -30,7 +31,7 @@
 #else
 #define SPN_TILE_MINB_G 4
 #define SPN_TILE_MINB_S 3
-#define SPN_TILE_MINB_GS 2
+#define SPN_TILE_MINB_GS 4
 #endif
 
 template <int MODE> struct TileGeom;

@@ -21,6 +21,7 @@
 // grid of full-occupancy CTAs keeps >50 KB per SM in flight.
 // HBM-bound (4 B index + 8..16 B payload per nnz): no tensor cores.
 #pragma once
+#include <type_traits>
 #include "ogs_kernels.cuh"
 
 namespace spn {
@@ -76,6 +77,22 @@ __device__ __forceinline__ void fold_step<double, SPN_ADD>(double& acc, double y
   asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %3, %4;\n\t@p add.rn.f64 %0, %1, %2;\n\t}"
       : "+d"(acc) : "d"(y), "d"(x), "r"(pos), "r"(t));
 }
+// fold round with a ROUND-INVARIANT predicate: every lane that is not the head of its row recomputes
+// prefix(left neighbour) (+) own value in every round.  After round t the lanes at positions <= t hold their final
+// prefix (induction on the position), later rounds recompute the same bits, and heads never change — so the result
+// equals the position-by-position form above, without the per-round compare and the two 64-bit selects.
+template <typename T, int OP>
+__device__ __forceinline__ void fold_round(T& acc, T y, const T x, bool nonhead) {
+  OgsOp<T, OP>::apply(y, x);
+  if (nonhead) acc = y;
+}
+// FP64 Add without any select: heads shuffle from THEMSELVES (delta 0) and add +0.0, which leaves their prefix
+// bit-for-bit unchanged — a prefix is the result of identity + x0 (+ ...), hence never -0.0, and p + (+0.0) == p for
+// every other double (NaNs are already quiet).  Two SHFL + one DADD per round.
+__device__ __forceinline__ void fold_round_add_f64(double& acc, double xeff, int delta) {
+  acc = __shfl_up_sync(0xffffffffu, acc, delta) + xeff;
+}
+
 template <typename T>
 __device__ __forceinline__ T shfl_idx(T x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 
@@ -88,6 +105,19 @@ __device__ __forceinline__ unsigned ld_ids(const unsigned* p) {
   unsigned r;
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
+}
+
+// column of a packed id word.  The AND is opaque PTX on purpose: when the compiler sees the mask it folds it into
+// the 64-bit address arithmetic of EVERY indexed access as a six-instruction shift / mask / carry sequence (and
+// re-reads the base pointer from the constant bank under a predicate) — 12 of the ~80 instructions per tile.
+// With an opaque 32-bit column, `base + col` is one IMAD.WIDE.U32 and the access stays an LDG / STG.
+// (Used by the gather+scatter kernel; the gather kernel at its 64-register budget spills with it and keeps the plain mask.)
+template <bool OPAQUE>
+__device__ __forceinline__ unsigned col_of(unsigned w) {
+  if (!OPAQUE) return w & 0x7fffffffu;
+  unsigned c;
+  asm("and.b32 %0, %1, 0x7fffffff;" : "=r"(c) : "r"(w));
+  return c;
 }
 
 // experiment knobs (OGS_PROBE in tools/quick_ogs.py): VAR bit1 = plain instead of streaming
@@ -285,7 +315,7 @@ ogs_tile_pf_kernel(int NTall, int chunkTiles, const unsigned* __restrict__ colP,
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      xc[u] = (wc[u] != kEmptyLane) ? ld_once<T>(in + (wc[u] & 0x7fffffffu)) : OgsOp<T, OP>::init();
+      xc[u] = (wc[u] != kEmptyLane) ? ld_once<T>(in + col_of<MODE == TILE_GATHER_SCATTER>(wc[u])) : OgsOp<T, OP>::init();
   }
 
   while (true) {
@@ -302,7 +332,7 @@ ogs_tile_pf_kernel(int NTall, int chunkTiles, const unsigned* __restrict__ colP,
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        x1[u] = (w1[u] != kEmptyLane) ? ld_once<T>(in + (w1[u] & 0x7fffffffu)) : OgsOp<T, OP>::init();
+        x1[u] = (w1[u] != kEmptyLane) ? ld_once<T>(in + col_of<MODE == TILE_GATHER_SCATTER>(w1[u])) : OgsOp<T, OP>::init();
     }
 
     // ---- row structure of the current tiles from the sign bits
@@ -321,9 +351,27 @@ ogs_tile_pf_kernel(int NTall, int chunkTiles, const unsigned* __restrict__ colP,
     }
     // (VAR 8 / 16: timing probes that force 0 / 7 rounds — results are then wrong)
     const int R = (VAR & 8) ? 0 : (VAR & 16) ? 7 : __reduce_max_sync(0xffffffffu, maxpos);
-    for (int t = 1; t <= R; ++t) {
+    if constexpr (sizeof(T) == 8 && OP == SPN_ADD && !std::is_integral<T>::value) {
+      double xeff[U];  // own value, or +0.0 on a row head
+      int delta[U];    // 1, or 0 on a row head
 #pragma unroll
-      for (int u = 0; u < U; ++u) fold_step<T, OP>(acc[u], shfl_up1(acc[u]), xc[u], pos[u], t);
+      for (int u = 0; u < U; ++u) {
+        xeff[u] = (pos[u] > 0) ? (double)xc[u] : 0.0;
+        delta[u] = (pos[u] > 0) ? 1 : 0;
+      }
+      for (int t = 1; t <= R; ++t) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          double a = (double)acc[u];
+          fold_round_add_f64(a, xeff[u], delta[u]);
+          acc[u] = (T)a;
+        }
+      }
+    } else {
+      for (int t = 1; t <= R; ++t) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) fold_round<T, OP>(acc[u], shfl_up1(acc[u]), xc[u], pos[u] > 0);
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -334,7 +382,7 @@ ogs_tile_pf_kernel(int NTall, int chunkTiles, const unsigned* __restrict__ colP,
       } else {
         const int lastlane = lane + __ffs(last[u] >> lane) - 1;
         const T total = shfl_idx(acc[u], lastlane & 31);
-        if (valid) __stcs(out + (wc[u] & 0x7fffffffu), total);
+        if (valid) __stcs(out + col_of<true>(wc[u]), total);
       }
     }
 
