@@ -170,7 +170,10 @@ int g_variant = 0;
 int g_probe = 0;
 // iterations a warp of the gather / gather+scatter tile kernel runs before its CTA retires (spn_debug_set key 4);
 // 0 = persistent grid.  Short-lived CTAs let the halo kernels of a partitioned mesh (higher-priority stream) in.
-int g_chunk_iters = 16;
+// Measured at 64^3 (profiles/r01_notes.md): gather+scatter 0.483 ms with 8 iterations per CTA vs 0.547 ms persistent;
+// gather 0.365 ms persistent vs 0.389 ms chunked — so gather stays persistent.
+int g_chunk_iters = 8;
+int g_chunk_iters_gather = 0;
 
 template <typename K>
 int resident_ctas(K kern, int threads, int* cache) {
@@ -261,7 +264,8 @@ int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaSt
       static int res = 0;
       rc = resident_ctas(kern, TH, &res);
       if (rc) return rc;
-      const int chunk = g_chunk_iters > 0 ? g_chunk_iters * (TH / 32) * U : 0;
+      const int iters = (MODE == TILE_GATHER) ? g_chunk_iters_gather : g_chunk_iters;
+      const int chunk = iters > 0 ? iters * (TH / 32) * U : 0;
       if (chunk > 0 && ctas_needed > res * d->sms)
         kern<<<(NT + chunk - 1) / chunk, TH, 0, st>>>(NT, chunk, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
       else
@@ -500,6 +504,7 @@ int spn_debug_set(int key, int value) {
   if (key == 2 && value >= 32) { g_slice_rows = value; return SPN_SUCCESS; }
   if (key == 3) { g_class_tiles = value; return SPN_SUCCESS; }
   if (key == 4 && value >= 0) { g_chunk_iters = value; return SPN_SUCCESS; }
+  if (key == 5 && value >= 0) { g_chunk_iters_gather = value; return SPN_SUCCESS; }
   return SPN_ERR_INVALID_ARGUMENT;
 }
 

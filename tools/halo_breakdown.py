@@ -56,7 +56,7 @@ def main():
         t5 = timed(5)
         if rank == 0:
             print(f"chunk iters {iters:3d}: full step {t*1e3:8.1f} us | interior only {t5*1e3:8.1f} us", flush=True)
-    KL.spn_debug_set(4, 16)
+    KL.spn_debug_set(4, 8)
     for mask in (0, 5, 6, 2, 4, 1, 0):
         if mask == 3:
             continue

@@ -45,6 +45,9 @@ def main():
     plan = K.OgsPlan(rs, d_rs, d_ci, Nt, colIds=None if os.environ.get("OGS_NO_GS_ORDER") else ci)
     print(f"plan: {plan.Ntiles} tiles ({Nt / max(plan.Ntiles, 1):.1f} nnz/tile), {plan.Nirregular} irregular rows, "
           f"{plan.plan_bytes / 1e6:.1f} MB, built in {time.time() - t0:.2f}s", flush=True)
+    if os.environ.get("OGS_CHUNK"):
+        from streamparanumal_b200 import _lib as _l
+        _l.kernel_lib().spn_debug_set(4, int(os.environ["OGS_CHUNK"]))
     tg = timeit(lambda: plan.gather(1, v, gv))
     ts = timeit(lambda: plan.scatter(1, gv, v))
     tgs = timeit(lambda: plan.gather_scatter(1, v), iters=50)
