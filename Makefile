@@ -8,7 +8,7 @@ CSRC      := streamparanumal_b200/csrc
 LIBDIR    := streamparanumal_b200/lib
 
 KERNEL_SRCS := $(CSRC)/runtime.cu $(CSRC)/stream_abi.cu $(CSRC)/ogs_abi.cu $(CSRC)/ogs_plan.cu $(CSRC)/ogs_halo.cu
-KERNEL_HDRS := $(CSRC)/common.cuh $(CSRC)/stream_kernels.cuh $(CSRC)/ogs_kernels.cuh $(CSRC)/ogs_pipe.cuh $(CSRC)/ogs_tile.cuh $(CSRC)/ogs_ctile.cuh include/spn_b200.h
+KERNEL_HDRS := $(CSRC)/common.cuh $(CSRC)/stream_kernels.cuh $(CSRC)/ogs_kernels.cuh $(CSRC)/ogs_pipe.cuh $(CSRC)/ogs_tile.cuh include/spn_b200.h
 
 all: $(LIBDIR)/libspn_b200.so $(LIBDIR)/libspn_b200_comm.so $(LIBDIR)/libspn_host.so bs
 

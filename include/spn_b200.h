@@ -176,9 +176,9 @@ int spn_ogs_extract(int N, int K, const int* ids, const void* q, void* gatherq, 
  * colIds + rowStarts + blockRowStarts.  Ncols is the operator's column count
  * (ogsOperator_t::Ncols: every colId < Ncols; vectors v have Ncols*K entries); the plan
  * also stores the inverse map column -> row, which turns Scatter into a streaming
- * kernel with coalesced stores.  h_colIds (host copy of colIds, may be NULL) lets the
- * plan give GatherScatter its own row order whose indexed stores complete whole
- * 32-byte sectors; without it GatherScatter walks the Gather tiles.  d_rowStarts / d_colIds are BORROWED device
+ * kernel with coalesced stores.  h_colIds (host copy of colIds) may be NULL: it is reserved
+ * for layouts that regroup rows on the host (two were measured and rejected this round,
+ * profiles/r01_notes.md).  d_rowStarts / d_colIds are BORROWED device
  * arrays that must outlive the plan.  The three calls are the device Gather /
  * Scatter / GatherScatter of libs/ogs/ogsOperator.cpp:176-204, 295-322, 442-481 for
  * one CSR (gather CSR == scatter CSR, i.e. every case of an Unsigned operator and
@@ -196,7 +196,8 @@ int spn_ogs_plan_gather_scatter(spn_ogs_plan_t plan, int K, void* v, int type, i
 /* out-of-place form: w[col] = OP_{col' in row(col)} v[col'] for every column of the operator
  * (entries of w outside the operator are left untouched) */
 int spn_ogs_plan_gather_scatter_to(spn_ogs_plan_t plan, int K, const void* v, void* w, int type, int op, spn_stream_t stream);
-/* tuning/experiment knob (key 0: kernel variant); not part of the drop-in surface */
+/* tuning/experiment knobs (key 4 / 5: iterations per CTA of the gather+scatter / gather tile kernel, 0 = persistent);
+ * not part of the drop-in surface */
 int spn_debug_set(int key, int value);
 
 /* ------------------------------------------------------------------------

@@ -4,9 +4,8 @@
 // ogs_tile.cuh) and its three kernels (libs/ogs/ogsOperator.cpp:176-204,295-322,442-481).
 #include <algorithm>
 #include <new>
-#include <thread>
 #include <vector>
-#include "ogs_ctile.cuh"
+#include "ogs_tile.cuh"
 
 // Launch geometry per operation, from the sweeps in profiles/r01_notes.md (B200, degree-7 hex; gather+scatter re-swept
 // after the instruction diet of the fold: U=4 with four resident CTAs beats U=8 with two, 0.487 vs 0.517 ms):
@@ -47,12 +46,6 @@ struct spn_ogs_plan {
   int nIrr;  // irregular rows
   long long nnz;
   unsigned* d_colP;  // packed ids, one 128-byte line per tile (owned)
-  // class-tile plan of the K==1 gather+scatter (ogs_ctile.cuh): rows of length <= 8 regrouped by length class
-  unsigned* d_ctIds;        // NTct * 256 ids (owned)
-  unsigned char* d_ctCls;   // log2(class length) per tile (owned)
-  int NTct;
-  unsigned* d_colPlong;     // ogs_tile.cuh tiles holding only the rows of length 9..32 (owned)
-  int NTlong;
   int* d_row0;       // first row of each tile (owned)
   int* d_irr;        // irregular rows (owned)
   int* d_rowOf;      // row of every column, -1 = none (owned); drives scatter
@@ -63,111 +56,6 @@ struct spn_ogs_plan {
 
 namespace {
 
-int g_slice_rows = kCtSliceRowsDefault;  // spn_debug_set key 2 (read at plan creation)
-// spn_debug_set key 3: build the class-tile layout (ogs_ctile.cuh) at plan creation.  OFF by default: measured
-// on B200 it is slower than the warp tiles (0.83 vs 0.53 ms at 64^3 degree 7) because regrouping rows by length
-// separates columns that share a 32-byte sector, which doubles the L2 sector traffic (profiles/r01_notes.md)
-int g_class_tiles = 0;
-
-// ---------------------------------------------------------------------------
-// Class-tile layout of the K==1 gather+scatter (ogs_ctile.cuh).  Rows of length 1..8 are
-// regrouped by length class {1,2,4,8} inside slices of kCtSliceRows consecutive rows; rows of
-// length 9..32 go to `longRows` (packed into ogs_tile.cuh tiles by the caller).  Host side,
-// one thread per range of slices.
-// ---------------------------------------------------------------------------
-inline int class_of(int len) { return len <= 1 ? 0 : len <= 2 ? 1 : len <= 4 ? 2 : 3; }
-
-void build_class_tiles(int Nrows, const int* rs, const int* ci, std::vector<unsigned>& ids,
-                       std::vector<unsigned char>& cls, std::vector<int>& longRows) {
-  const int kCtSliceRows = g_slice_rows;
-  const int nslices = (Nrows + kCtSliceRows - 1) / kCtSliceRows;
-  std::vector<long long> tileStart((size_t)nslices + 1, 0);
-  std::vector<std::vector<int>> longOf((size_t)nslices);
-  const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  auto parallel_slices = [&](auto&& body) {
-    std::vector<std::thread> th;
-    const int per = (nslices + (int)hw - 1) / (int)hw;
-    for (unsigned w = 0; w < hw; ++w) {
-      const int s0 = (int)w * per, s1 = std::min(nslices, s0 + per);
-      if (s0 >= s1) break;
-      th.emplace_back([=, &body]() { for (int sl = s0; sl < s1; ++sl) body(sl); });
-    }
-    for (auto& t : th) t.join();
-  };
-  // pass 1: tiles per slice
-  parallel_slices([&](int sl) {
-    const int r0 = sl * kCtSliceRows, r1 = std::min(Nrows, r0 + kCtSliceRows);
-    long long n[4] = {0, 0, 0, 0};
-    for (int r = r0; r < r1; ++r) {
-      const int len = rs[r + 1] - rs[r];
-      if (len >= 1 && len <= kCtLines) ++n[class_of(len)];
-      else if (len > kCtLines && len <= 32) longOf[sl].push_back(r);
-    }
-    long long tiles = 0;
-    for (int k = 0; k < 4; ++k) {
-      const long long rowsPerTile = 32 * (kCtLines >> k);
-      tiles += (n[k] + rowsPerTile - 1) / rowsPerTile;
-    }
-    tileStart[sl + 1] = tiles;
-  });
-  for (int sl = 0; sl < nslices; ++sl) tileStart[sl + 1] += tileStart[sl];
-  const long long NT = tileStart[nslices];
-  ids.assign((size_t)(NT + kCtPad) * kCtSlots, kEmptyLane);
-  cls.assign((size_t)(NT + kCtPad), 0);
-  // pass 2: fill
-  parallel_slices([&](int sl) {
-    const int r0 = sl * kCtSliceRows, r1 = std::min(Nrows, r0 + kCtSliceRows);
-    long long n[4] = {0, 0, 0, 0};
-    for (int r = r0; r < r1; ++r) {
-      const int len = rs[r + 1] - rs[r];
-      if (len >= 1 && len <= kCtLines) ++n[class_of(len)];
-    }
-    long long base[4], t = tileStart[sl];
-    for (int k = 0; k < 4; ++k) {
-      base[k] = t;
-      const long long rowsPerTile = 32 * (kCtLines >> k);
-      const long long nt = (n[k] + rowsPerTile - 1) / rowsPerTile;
-      for (long long i = 0; i < nt; ++i) cls[(size_t)(t + i)] = (unsigned char)k;
-      t += nt;
-    }
-    long long seen[4] = {0, 0, 0, 0};
-    for (int r = r0; r < r1; ++r) {
-      const int len = rs[r + 1] - rs[r];
-      if (len < 1 || len > kCtLines) continue;
-      const int k = class_of(len), L = 1 << k;
-      const long long m = seen[k]++;
-      const long long rowsPerTile = 32 * (kCtLines >> k);
-      const long long tile = base[k] + m / rowsPerTile;
-      const int within = (int)(m % rowsPerTile), g = within >> 5, lane = within & 31;
-      unsigned* dst = ids.data() + (size_t)tile * kCtSlots;
-      for (int sidx = 0; sidx < len; ++sidx) dst[(g * L + sidx) * 32 + lane] = (unsigned)ci[rs[r] + sidx];
-    }
-  });
-  longRows.clear();
-  for (int sl = 0; sl < nslices; ++sl) longRows.insert(longRows.end(), longOf[sl].begin(), longOf[sl].end());
-}
-
-// greedy packing of the given rows (each 1..32 long) into ogs_tile.cuh id lines
-void pack_rows_into_lines(const std::vector<int>& rows, const int* rs, const int* ci, std::vector<unsigned>& words) {
-  words.clear();
-  int cur_n = 0;
-  auto flush = [&]() {
-    if (cur_n > 0) words.resize(words.size() + (size_t)(32 - cur_n), kEmptyLane);
-    cur_n = 0;
-  };
-  for (int r : rows) {
-    const int len = rs[r + 1] - rs[r];
-    if (cur_n + len > 32) flush();
-    for (int g = rs[r]; g < rs[r + 1]; ++g) words.push_back((unsigned)ci[g] | (g == rs[r + 1] - 1 ? 0x80000000u : 0u));
-    cur_n += len;
-  }
-  flush();
-}
-
-// experiment knobs, see spn_debug_set.  g_variant: 0 default; 1 gather+scatter on the warp tiles
-// (ogs_tile.cuh) even when the plan has class tiles; 2 class tiles without the register pipeline
-int g_variant = 0;
-int g_probe = 0;
 // iterations a warp of the gather / gather+scatter tile kernel runs before its CTA retires (spn_debug_set key 4);
 // 0 = persistent grid.  Short-lived CTAs let the halo kernels of a partitioned mesh (higher-priority stream) in.
 // Measured at 64^3 (profiles/r01_notes.md): gather+scatter 0.483 ms with 8 iterations per CTA vs 0.547 ms persistent;
@@ -185,75 +73,13 @@ int resident_ctas(K kern, int threads, int* cache) {
   return SPN_SUCCESS;
 }
 
-#ifndef SPN_CT_THREADS
-#define SPN_CT_THREADS 256
-#endif
-#ifndef SPN_CT_MINB
-#define SPN_CT_MINB 3
-#endif
-#ifndef SPN_CT_MINB_SIMPLE
-#define SPN_CT_MINB_SIMPLE 5
-#endif
-
-// K==1 gather+scatter on the class tiles (+ the long-row warp tiles)
-template <typename T, int OP>
-int launch_class_tiles(const spn_ogs_plan* p, const void* in, void* out, cudaStream_t st, DeviceInfo* d) {
-  constexpr int TH = SPN_CT_THREADS;
-  if (p->NTct > 0) {
-    const int ctas_needed = (p->NTct + TH / 32 - 1) / (TH / 32);
-    if (g_variant == 6) {
-      auto kern = ogs_ctile_gs_kernel<T, OP, TH, SPN_CT_MINB_SIMPLE, 2>;
-      static int res = 0;
-      int rc = resident_ctas(kern, TH, &res);
-      if (rc) return rc;
-      kern<<<std::min(ctas_needed, res * d->sms), TH, 0, st>>>(p->NTct, p->d_ctIds, p->d_ctCls, static_cast<const T*>(in), static_cast<T*>(out));
-    } else if (g_variant == 4) {
-      auto kern = ogs_ctile_gs_pf_kernel<T, OP, TH, SPN_CT_MINB, 2>;
-      static int res = 0;
-      int rc = resident_ctas(kern, TH, &res);
-      if (rc) return rc;
-      kern<<<std::min(ctas_needed, res * d->sms), TH, 0, st>>>(p->NTct, p->d_ctIds, p->d_ctCls, static_cast<const T*>(in), static_cast<T*>(out));
-    } else if (g_variant == 2) {
-      auto kern = ogs_ctile_gs_kernel<T, OP, TH, SPN_CT_MINB_SIMPLE>;
-      static int res = 0;
-      int rc = resident_ctas(kern, TH, &res);
-      if (rc) return rc;
-      kern<<<std::min(ctas_needed, res * d->sms), TH, 0, st>>>(p->NTct, p->d_ctIds, p->d_ctCls, static_cast<const T*>(in), static_cast<T*>(out));
-    } else {
-      auto kern = ogs_ctile_gs_pf_kernel<T, OP, TH, SPN_CT_MINB>;
-      static int res = 0;
-      int rc = resident_ctas(kern, TH, &res);
-      if (rc) return rc;
-      kern<<<std::min(ctas_needed, res * d->sms), TH, 0, st>>>(p->NTct, p->d_ctIds, p->d_ctCls, static_cast<const T*>(in), static_cast<T*>(out));
-    }
-    SPN_LAUNCH_CHECK();
-  }
-  if (p->NTlong > 0) {
-    constexpr int U = 2, LTH = 256;
-    auto kern = ogs_tile_kernel<T, OP, TILE_GATHER_SCATTER, U, true, LTH, 2>;
-    static int res = 0;
-    int rc = resident_ctas(kern, LTH, &res);
-    if (rc) return rc;
-    const int warps_needed = (p->NTlong + U - 1) / U;
-    const int ctas_needed = (warps_needed + LTH / 32 - 1) / (LTH / 32);
-    kern<<<std::min(ctas_needed, res * d->sms), LTH, 0, st>>>(p->NTlong, 1, p->d_colPlong, nullptr, static_cast<const T*>(in), static_cast<T*>(out));
-    SPN_LAUNCH_CHECK();
-  }
-  return SPN_SUCCESS;
-}
-
 template <typename T, int OP, int MODE>
 int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaStream_t st) {
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  const bool class_tiles = (MODE == TILE_GATHER_SCATTER) && K == 1 && p->d_ctIds != nullptr && g_variant != 1;
-  if (class_tiles) {
-    rc = launch_class_tiles<T, OP>(p, in, out, st, d);
-    if (rc) return rc;
-  }
   const unsigned* colP = p->d_colP;
-  const int NT = class_tiles ? 0 : p->NT;
+  const int NT = p->NT;
   if (NT > 0) {
     constexpr int U = TileGeom<MODE>::U, TH = SPN_TILE_THREADS, MB = TileGeom<MODE>::MINB;
     const int warps_needed = (NT + U - 1) / U;
@@ -336,11 +162,6 @@ int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h
   p->d_row0 = nullptr;
   p->d_irr = nullptr;
   p->d_rowOf = nullptr;
-  p->d_ctIds = nullptr;
-  p->d_ctCls = nullptr;
-  p->NTct = 0;
-  p->d_colPlong = nullptr;
-  p->NTlong = 0;
   p->Ncols = Ncols;
 
   // greedy packing of whole consecutive rows into <=32-nnz tiles
@@ -390,25 +211,7 @@ int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h
     SPN_CUDA_TRY(cudaMalloc(&p->d_irr, sizeof(int) * irr.size()));
     SPN_CUDA_TRY(cudaMemcpy(p->d_irr, irr.data(), sizeof(int) * irr.size(), cudaMemcpyHostToDevice));
   }
-  if (g_class_tiles && h_colIds && Ncols > 0 && p->NT > 0) {
-    // class tiles for the K==1 gather+scatter (needs the host copy of colIds)
-    std::vector<unsigned> ids, words;
-    std::vector<unsigned char> cls;
-    std::vector<int> longRows;
-    build_class_tiles(Nrows, h_rowStarts, h_colIds, ids, cls, longRows);
-    p->NTct = (int)(cls.size() - kCtPad);
-    SPN_CUDA_TRY(cudaMalloc(&p->d_ctIds, sizeof(unsigned) * ids.size()));
-    SPN_CUDA_TRY(cudaMemcpy(p->d_ctIds, ids.data(), sizeof(unsigned) * ids.size(), cudaMemcpyHostToDevice));
-    SPN_CUDA_TRY(cudaMalloc(&p->d_ctCls, cls.size()));
-    SPN_CUDA_TRY(cudaMemcpy(p->d_ctCls, cls.data(), cls.size(), cudaMemcpyHostToDevice));
-    if (!longRows.empty()) {
-      pack_rows_into_lines(longRows, h_rowStarts, h_colIds, words);
-      p->NTlong = (int)(words.size() / 32);
-      words.resize(words.size() + (size_t)32 * kTilePad, kEmptyLane);
-      SPN_CUDA_TRY(cudaMalloc(&p->d_colPlong, sizeof(unsigned) * words.size()));
-      SPN_CUDA_TRY(cudaMemcpy(p->d_colPlong, words.data(), sizeof(unsigned) * words.size(), cudaMemcpyHostToDevice));
-    }
-  }
+  (void)h_colIds;  // reserved for layouts that need the host copy of the ids (none in use: profiles/r01_notes.md)
   if (Ncols > 0) {
     // inverse map for scatter: rowOf[c] = row holding column c, -1 if none
     SPN_CUDA_TRY(cudaMalloc(&p->d_rowOf, sizeof(int) * (size_t)Ncols));
@@ -433,9 +236,6 @@ int spn_ogs_plan_destroy(spn_ogs_plan_t plan) {
   if (plan->d_colP) cudaFree(plan->d_colP);
   if (plan->d_row0) cudaFree(plan->d_row0);
   if (plan->d_rowOf) cudaFree(plan->d_rowOf);
-  if (plan->d_ctIds) cudaFree(plan->d_ctIds);
-  if (plan->d_ctCls) cudaFree(plan->d_ctCls);
-  if (plan->d_colPlong) cudaFree(plan->d_colPlong);
   if (plan->d_irr) cudaFree(plan->d_irr);
   delete plan;
   return SPN_SUCCESS;
@@ -447,9 +247,7 @@ int spn_ogs_plan_info(spn_ogs_plan_t plan, int* Ntiles, int* Nirregular, size_t*
   if (Nirregular) *Nirregular = plan->nIrr;
   if (plan_bytes)
     *plan_bytes = (sizeof(unsigned) * 32 + sizeof(int)) * (size_t)(plan->NT + kTilePad) + sizeof(int) * (size_t)plan->nIrr +
-                  sizeof(int) * (size_t)plan->Ncols +
-                  (plan->d_ctIds ? (sizeof(unsigned) * kCtSlots + 1) * (size_t)(plan->NTct + kCtPad) : 0) +
-                  (plan->d_colPlong ? sizeof(unsigned) * 32 * (size_t)(plan->NTlong + kTilePad) : 0);
+                  sizeof(int) * (size_t)plan->Ncols;
   return SPN_SUCCESS;
 }
 
@@ -499,10 +297,6 @@ int spn_ogs_plan_scatter(spn_ogs_plan_t plan, int K, const void* gv, void* v, in
 }
 
 int spn_debug_set(int key, int value) {
-  if (key == 0) { g_variant = value; return SPN_SUCCESS; }
-  if (key == 1) { g_probe = value; return SPN_SUCCESS; }
-  if (key == 2 && value >= 32) { g_slice_rows = value; return SPN_SUCCESS; }
-  if (key == 3) { g_class_tiles = value; return SPN_SUCCESS; }
   if (key == 4 && value >= 0) { g_chunk_iters = value; return SPN_SUCCESS; }
   if (key == 5 && value >= 0) { g_chunk_iters_gather = value; return SPN_SUCCESS; }
   return SPN_ERR_INVALID_ARGUMENT;

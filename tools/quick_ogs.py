@@ -53,22 +53,6 @@ def main():
     tgs = timeit(lambda: plan.gather_scatter(1, v), iters=50)
     print(f"tile plan: gather {tg*1e3:.3f} ms {b6/tg*1e-9:7.1f} GB/s | scatter {ts*1e3:.3f} ms {b6/ts*1e-9:7.1f} GB/s | "
           f"gatherScatter {tgs*1e3:.3f} ms {b8/tgs*1e-9:7.1f} GB/s {Ng/tgs*1e-9:6.1f} GDOF/s", flush=True)
-    from streamparanumal_b200 import _lib
-    L = _lib.kernel_lib()
-    names = {0: "class tiles pipelined .cs stores", 2: "class tiles simple .cs", 4: "class tiles pipelined plain stores",
-             6: "class tiles simple plain stores", 1: "warp tiles (ogs_tile.cuh)"}
-    L.spn_debug_set(3, 1)
-    for sr in [int(x) for x in os.environ.get("OGS_SLICES", "65536").split(",")]:
-        L.spn_debug_set(2, sr)
-        pl = K.OgsPlan(rs, d_rs, d_ci, Nt, colIds=ci)
-        for var in (0, 2, 4, 6, 1):
-            L.spn_debug_set(0, var)
-            t = timeit(lambda: pl.gather_scatter(1, v), iters=50)
-            print(f"slice {sr:7d} variant {var} [{names[var]}]: {t*1e3:.3f} ms {b8/t*1e-9:7.1f} GB/s {Ng/t*1e-9:6.1f} GDOF/s", flush=True)
-        L.spn_debug_set(0, 0)
-        pl.close()
-    L.spn_debug_set(2, 65536)
-    L.spn_debug_set(3, 0)
     for lim in limits:
         bs = util.greedy_blocks(rs, lim)
         nb = bs.size - 1
