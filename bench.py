@@ -383,7 +383,7 @@ def run_b200(args):
                    "l2": "q (1.07 GB) + ids (0.54 GB) per call exceed the 126 MB L2; no flush needed",
                    "host_setup_s": round(t_setup, 2)},
         "effective_gbs": bytes_step / t_step * 1e-9,
-        "roofline": {"bound": "hbm", "kernel": "ogs_tile_pf_kernel<double,Add,GATHER_SCATTER,U=4,256 threads,4 CTAs/SM>",
+        "roofline": {"bound": "hbm", "kernel": "ogs_tile_pf_kernel<double,Add,GATHER_SCATTER,U=4,128 threads,8 CTAs/SM>",
                      "achieved": bytes_rank / t_step * 1e-9, "peak": peak, "peak_source": peak_src,
                      "unit": "GB/s", "frac": bytes_rank / t_step * 1e-9 / peak,
                      "frac_of_8TBs_nominal": bytes_rank / t_step * 1e-9 / 8000.0,

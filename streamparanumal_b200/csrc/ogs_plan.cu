@@ -33,10 +33,24 @@
 #define SPN_TILE_MINB_GS 4
 #endif
 
+// CTA size per operation (last sweep of the round, profiles/r01_notes.md): at equal registers per SM, gather is
+// fastest with 512-thread CTAs (0.354 ms), gather+scatter with 128-thread CTAs (0.477 ms).
+#ifdef SPN_TILE_THREADS_ALL
+#define SPN_TILE_TH_G SPN_TILE_THREADS_ALL
+#define SPN_TILE_TH_GS SPN_TILE_THREADS_ALL
+#define SPN_TILE_CTAS_G SPN_TILE_MINB_G
+#define SPN_TILE_CTAS_GS SPN_TILE_MINB_GS
+#else
+#define SPN_TILE_TH_G 512
+#define SPN_TILE_TH_GS 128
+#define SPN_TILE_CTAS_G (SPN_TILE_MINB_G * 256 / 512)
+#define SPN_TILE_CTAS_GS (SPN_TILE_MINB_GS * 256 / 128)
+#endif
+
 template <int MODE> struct TileGeom;
-template <> struct TileGeom<spn::TILE_GATHER> { static constexpr int U = SPN_TILE_U_G, MINB = SPN_TILE_MINB_G; };
-template <> struct TileGeom<spn::TILE_SCATTER> { static constexpr int U = SPN_TILE_U_S, MINB = SPN_TILE_MINB_S; };
-template <> struct TileGeom<spn::TILE_GATHER_SCATTER> { static constexpr int U = SPN_TILE_U_GS, MINB = SPN_TILE_MINB_GS; };
+template <> struct TileGeom<spn::TILE_GATHER> { static constexpr int U = SPN_TILE_U_G, MINB = SPN_TILE_MINB_G, PF_TH = SPN_TILE_TH_G, PF_MINB = SPN_TILE_CTAS_G; };
+template <> struct TileGeom<spn::TILE_SCATTER> { static constexpr int U = SPN_TILE_U_S, MINB = SPN_TILE_MINB_S, PF_TH = SPN_TILE_THREADS, PF_MINB = SPN_TILE_MINB_S; };
+template <> struct TileGeom<spn::TILE_GATHER_SCATTER> { static constexpr int U = SPN_TILE_U_GS, MINB = SPN_TILE_MINB_GS, PF_TH = SPN_TILE_TH_GS, PF_MINB = SPN_TILE_CTAS_GS; };
 
 using namespace spn;
 
@@ -86,16 +100,18 @@ int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaSt
     const int ctas_needed = (warps_needed + TH / 32 - 1) / (TH / 32);
     if (K == 1 && MODE != TILE_SCATTER) {
       constexpr int M2 = (MODE == TILE_SCATTER) ? TILE_GATHER : MODE;  // (scatter never reaches this kernel)
-      auto kern = ogs_tile_pf_kernel<T, OP, M2, U, TH, MB>;
+      constexpr int PTH = TileGeom<MODE>::PF_TH, PMB = TileGeom<MODE>::PF_MINB;
+      auto kern = ogs_tile_pf_kernel<T, OP, M2, U, PTH, PMB>;
       static int res = 0;
-      rc = resident_ctas(kern, TH, &res);
+      rc = resident_ctas(kern, PTH, &res);
       if (rc) return rc;
+      const int pf_ctas_needed = (warps_needed + PTH / 32 - 1) / (PTH / 32);
       const int iters = (MODE == TILE_GATHER) ? g_chunk_iters_gather : g_chunk_iters;
-      const int chunk = iters > 0 ? iters * (TH / 32) * U : 0;
-      if (chunk > 0 && ctas_needed > res * d->sms)
-        kern<<<(NT + chunk - 1) / chunk, TH, 0, st>>>(NT, chunk, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+      const int chunk = iters > 0 ? iters * (PTH / 32) * U : 0;  // every warp of the CTA runs `iters` iterations
+      if (chunk > 0 && pf_ctas_needed > res * d->sms)
+        kern<<<(NT + chunk - 1) / chunk, PTH, 0, st>>>(NT, chunk, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
       else
-        kern<<<std::min(ctas_needed, res * d->sms), TH, 0, st>>>(NT, 0, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
+        kern<<<std::min(pf_ctas_needed, res * d->sms), PTH, 0, st>>>(NT, 0, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
     } else if (K == 1) {
       auto kern = ogs_tile_kernel<T, OP, MODE, U, true, TH, MB>;
       static int res = 0;
