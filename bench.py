@@ -47,7 +47,7 @@ def bs8_bytes(Nt, Ng):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one BS8 launch at the headline size, from the ncu --set full
 # capture summarised in profiles/ (None until a capture at this size is committed)
-TRAFFIC_BS8 = 2652936000  # profiles/r01_ncu_full_summary_f.txt: 1.619144 GB read + 1.033792 GB written (64^3, degree 7)
+TRAFFIC_BS8 = 2639159000  # profiles/r01_ncu_full_summary_f3_ogs.txt: 1.611656 GB read + 1.027503 GB written (64^3, degree 7)
 
 
 def bs6_bytes(Nt, Ng):
