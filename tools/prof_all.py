@@ -1,5 +1,5 @@
 """Launch every hot-path kernel a few times at a roofline-relevant size (run under ncu on the
-GPU box: tools/gpu_r1k.sh).  Sizes: streaming kernels N=2^26 FP64 (BS5 config 1), ogs on a
+GPU box: tools/gpu_pass_1gpu.sh).  Sizes: streaming kernels N=2^26 FP64 (BS5 config 1), ogs on a
 degree-7 hex box of nx^3 elements (default 48; the headline 64^3 mesh under bench.py)."""
 import os
 import sys
