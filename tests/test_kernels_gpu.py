@@ -307,3 +307,44 @@ def test_ogs_properties_at_scale(K):
     gs2 = gs.clone()
     K.ogs_gather_scatter(nb, 1, d_bs, d_rs, d_ci, d_rs, d_ci, gs2)
     assert torch.equal(gs2, gs * torch.from_numpy(mult).cuda())
+
+
+def test_ogs_signed_zeros_and_infinities_bit_patterns(K, oracle):
+    # 0.0 + (-0.0) = +0.0 is what the reference computes for every row (fold starts from the identity), and the
+    # select-free FP64 fold rounds of the tile kernels (row heads add +0.0) rely on a prefix never being -0.0:
+    # compare BIT PATTERNS, not values, on data full of -0.0, +0.0 and infinities
+    ids = util.hex_ids(3, 3, 2, 7)
+    rs, ci = util.csr_from_ids(ids)
+    n = ids.size
+    v = util.splitmix64(n, 77)
+    pick = np.arange(n)
+    v[pick % 3 == 0] = -0.0
+    v[pick % 7 == 1] = 0.0
+    v[pick % 101 == 5] = np.inf
+    v[pick % 103 == 6] = -np.inf   # +inf + -inf rows give NaN on both sides: compared as bits only where not NaN
+    d_rs, d_ci = dev(rs), dev(ci)
+    plan = K.OgsPlan(rs, d_rs, d_ci, n, colIds=ci)
+    bs = util.greedy_blocks(rs, K.nodes_per_block())
+    d_bs = dev(bs)
+    g_ref = oracle.ogs_gather(rs, ci, v)
+    gs_ref = oracle.ogs_gather_scatter(rs, ci, rs, ci, v)
+
+    def same_bits(got, ref):
+        got, ref = np.asarray(got), np.asarray(ref)
+        nan = np.isnan(ref)
+        assert np.array_equal(np.isnan(got), nan)
+        return np.array_equal(got[~nan].view(np.int64), ref[~nan].view(np.int64))
+
+    assert (g_ref.view(np.int64) == np.float64(-0.0).view(np.int64)).sum() == 0   # no row total is -0.0
+    dg = torch.empty(rs.size - 1, dtype=torch.float64, device="cuda")
+    plan.gather(1, dev(v), dg)
+    assert same_bits(dg.cpu().numpy(), g_ref)
+    K.ogs_gather(bs.size - 1, 1, d_bs, d_rs, d_ci, dev(v), dg)
+    assert same_bits(dg.cpu().numpy(), g_ref)
+    dq = dev(v)
+    plan.gather_scatter(1, dq)
+    assert same_bits(dq.cpu().numpy(), gs_ref)
+    dq = dev(v)
+    K.ogs_gather_scatter(bs.size - 1, 1, d_bs, d_rs, d_ci, d_rs, d_ci, dq)
+    assert same_bits(dq.cpu().numpy(), gs_ref)
+    plan.close()
