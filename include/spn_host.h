@@ -47,7 +47,8 @@ int spn_host_box_hex_ids(int rank, int size, int nx, int ny, int nz, int p, long
 
 /* ---- ogs_t (include/ogs.hpp:216-341) --------------------------------------------------------------- */
 typedef struct spn_host_ogs* spn_host_ogs_t;
-/* ogs_t::Setup(N, ids, comm, kind, method, unique, verbose, platform).  kind: 0 Unsigned, 1 Signed.
+/* ogs_t::Setup(N, ids, comm, kind, method, unique, verbose, platform).  kind: 0 Unsigned, 1 Signed, 2 Halo (halo_t::Setup:
+ * ids > 0 = the owned copy of a node, ids < 0 = halo copies; only spn_host_halo_* may be called on such a handle).
  * platform NULL: host-only plan (no CUDA call), used to test the partition/exchange logic on CPU. */
 int spn_host_ogs_setup(spn_host_ogs_t* ogs, int N, long long* ids, spn_host_comm_t comm, int kind, int unique,
                        int verbose, spn_host_platform_t platform);
@@ -77,6 +78,15 @@ int spn_host_ogs_gather_scatter_host_start(spn_host_ogs_t ogs, void* h_v, int k,
 int spn_host_ogs_gather_scatter_host_finish(spn_host_ogs_t ogs, void* h_v);
 int spn_host_ogs_gather(spn_host_ogs_t ogs, void* d_gv, const void* d_v, int k, int type, int op, int trans);
 int spn_host_ogs_scatter(spn_host_ogs_t ogs, void* d_v, const void* d_gv, int k, int type, int trans);
+
+/* halo_t::{Exchange,Combine}{,Start,Finish}(deviceMemory<T>, k) (include/ogs.hpp:347-397, libs/ogs/ogsHalo.cpp:39-400) on a handle
+ * set up with kind 2: Exchange copies the owner's value to every halo copy, Combine adds every copy into the owner. */
+int spn_host_halo_exchange(spn_host_ogs_t halo, void* d_v, int k, int type);
+int spn_host_halo_exchange_start(spn_host_ogs_t halo, void* d_v, int k, int type);
+int spn_host_halo_exchange_finish(spn_host_ogs_t halo, void* d_v, int k, int type);
+int spn_host_halo_combine(spn_host_ogs_t halo, void* d_v, int k, int type);
+int spn_host_halo_combine_start(spn_host_ogs_t halo, void* d_v, int k, int type);
+int spn_host_halo_combine_finish(spn_host_ogs_t halo, void* d_v, int k, int type);
 
 /* timing probes (key 0: bit mask of ogs_t::GatherScatter phases to skip); not part of the drop-in surface */
 int spn_host_debug_set(int key, int value);

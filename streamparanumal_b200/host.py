@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 
 SYM, NOTRANS, TRANS = 0, 1, 2            # ogs::Transpose
-UNSIGNED, SIGNED = 0, 1                  # ogs::Kind
+UNSIGNED, SIGNED, HALO = 0, 1, 2         # ogs::Kind
 ADD, MUL, MAX, MIN = 0, 1, 2, 3          # ogs::Op
 FLOAT, DOUBLE, INT32, INT64 = 0, 1, 2, 3  # ogs::Type
 
@@ -46,6 +46,12 @@ _HOST_SIGNATURES = {
     "spn_host_ogs_gather_scatter_host_start": [c_void_p, c_void_p, c_int, c_int, c_int, c_int],
     "spn_host_ogs_gather_scatter_host_finish": [c_void_p, c_void_p],
     "spn_host_debug_set": [c_int, c_int],
+    "spn_host_halo_exchange": [c_void_p, c_void_p, c_int, c_int],
+    "spn_host_halo_exchange_start": [c_void_p, c_void_p, c_int, c_int],
+    "spn_host_halo_exchange_finish": [c_void_p, c_void_p, c_int, c_int],
+    "spn_host_halo_combine": [c_void_p, c_void_p, c_int, c_int],
+    "spn_host_halo_combine_start": [c_void_p, c_void_p, c_int, c_int],
+    "spn_host_halo_combine_finish": [c_void_p, c_void_p, c_int, c_int],
     "spn_host_ogs_gather": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int],
     "spn_host_ogs_scatter": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int],
 }
@@ -156,6 +162,7 @@ class Ogs:
     def __init__(self, ids, comm, kind=SIGNED, unique=True, verbose=False, platform=None):
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         self.ids = ids
+        self.kind = int(kind)
         self.comm, self.platform = comm, platform
         self._h = c_void_p()
         _check(host_lib().spn_host_ogs_setup(byref(self._h), ids.size, ids.ctypes.data, comm._h, int(kind), int(bool(unique)),
@@ -215,6 +222,15 @@ class Ogs:
 
     def HostGatherScatterFinish(self, h_ptr):
         _check(host_lib().spn_host_ogs_gather_scatter_host_finish(self._h, h_ptr), "HostGatherScatterFinish")
+
+    # ---- halo_t operations (handles set up with kind=HALO) ----
+    def HaloExchange(self, v, k=1):
+        self._sync_stream()
+        _check(host_lib().spn_host_halo_exchange(self._h, v.data_ptr(), k, self._type(v)), "halo_t::Exchange")
+
+    def HaloCombine(self, v, k=1):
+        self._sync_stream()
+        _check(host_lib().spn_host_halo_combine(self._h, v.data_ptr(), k, self._type(v)), "halo_t::Combine")
 
     def Gather(self, gv, v, k=1, op=ADD, trans=TRANS):
         self._sync_stream()

@@ -192,6 +192,22 @@ int spn_host_debug_set(int key, int value) {
   if (key == 0) { spn::ogs::g_debug_skip = value; return SPN_SUCCESS; }
   return SPN_ERR_INVALID_ARGUMENT;
 }
+// halo_t operations on an ogs handle set up with kind 2 (Halo): Exchange = owner value to every copy, Combine = every
+// copy added into the owner (libs/ogs/ogsHalo.cpp:39-400)
+static int halo_op(spn_host_ogs_t h, void* v, int k, int type, int trans, int phase) {
+  if (!h) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] {
+    SPN_ABORT("halo operation on an ogs_t that was not set up with Kind Halo", !h->ogs.halo_only);
+    if (phase != 2) h->ogs.GatherScatterStart(v, k, (ogs::Type)type, ogs::Add, (ogs::Transpose)trans);
+    if (phase != 1) h->ogs.GatherScatterFinish(v, k, (ogs::Type)type, ogs::Add, (ogs::Transpose)trans);
+  });
+}
+int spn_host_halo_exchange(spn_host_ogs_t h, void* d_v, int k, int type) { return halo_op(h, d_v, k, type, ogs::NoTrans, 0); }
+int spn_host_halo_exchange_start(spn_host_ogs_t h, void* d_v, int k, int type) { return halo_op(h, d_v, k, type, ogs::NoTrans, 1); }
+int spn_host_halo_exchange_finish(spn_host_ogs_t h, void* d_v, int k, int type) { return halo_op(h, d_v, k, type, ogs::NoTrans, 2); }
+int spn_host_halo_combine(spn_host_ogs_t h, void* d_v, int k, int type) { return halo_op(h, d_v, k, type, ogs::Trans, 0); }
+int spn_host_halo_combine_start(spn_host_ogs_t h, void* d_v, int k, int type) { return halo_op(h, d_v, k, type, ogs::Trans, 1); }
+int spn_host_halo_combine_finish(spn_host_ogs_t h, void* d_v, int k, int type) { return halo_op(h, d_v, k, type, ogs::Trans, 2); }
 int spn_host_ogs_gather(spn_host_ogs_t h, void* gv, const void* v, int k, int type, int op, int trans) {
   if (!h) return SPN_ERR_INVALID_ARGUMENT;
   return guarded([&] {

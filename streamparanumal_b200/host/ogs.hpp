@@ -107,6 +107,7 @@ class ogs_t {
   bool unique = false;
   bool gather_defined = false;
   bool on_device = false;
+  bool halo_only = false;  // Kind Halo: only the rows shared between ranks act (no interior operator)
   bool peer_exchange() const { return p2p.enabled; }  // true: halo data moves by P2P stores over NVLink, false: NCCL
 
   std::shared_ptr<ogsOperator_t> gatherLocal, gatherHalo;
@@ -233,6 +234,30 @@ class ogs_t {
   HostStage stage[2];
   int nextStage = 0;
   spn_stream_t h2dStream = nullptr, d2hStream = nullptr;
+};
+
+// halo_t (include/ogs.hpp:347-397): element-halo exchange.  ids > 0 marks the one owned copy of a node, ids < 0 its
+// halo copies on other ranks (or this one); Exchange sends the owner's value to every copy, Combine adds every copy
+// into the owner.  Device-buffer versions only (the host-memory overloads of the reference run on the CPU).
+class halo_t {
+ public:
+  dlong Nhalo = 0;  // NhaloT - NhaloP: rows whose owner is another rank
+  ogs_t ogs;        // the Kind-Halo operator underneath
+
+  void Setup(const dlong N, hlong* ids, comm_t comm, const Method method, const bool verbose, platform_t& platform);
+  void SetupHost(const dlong N, hlong* ids, comm_t comm, const bool verbose);  // host-only plan, for CPU tests
+
+  void ExchangeStart(void* o_v, int k, Type type);
+  void ExchangeFinish(void* o_v, int k, Type type);
+  void CombineStart(void* o_v, int k, Type type);
+  void CombineFinish(void* o_v, int k, Type type);
+
+  template <typename T> void Exchange(deviceMemory<T> o_v, const int k) { ExchangeStart(o_v, k); ExchangeFinish(o_v, k); }
+  template <typename T> void ExchangeStart(deviceMemory<T> o_v, const int k) { ExchangeStart(o_v.ptr(), k, ogsType<T>::get()); }
+  template <typename T> void ExchangeFinish(deviceMemory<T> o_v, const int k) { ExchangeFinish(o_v.ptr(), k, ogsType<T>::get()); }
+  template <typename T> void Combine(deviceMemory<T> o_v, const int k) { CombineStart(o_v, k); CombineFinish(o_v, k); }
+  template <typename T> void CombineStart(deviceMemory<T> o_v, const int k) { CombineStart(o_v.ptr(), k, ogsType<T>::get()); }
+  template <typename T> void CombineFinish(deviceMemory<T> o_v, const int k) { CombineFinish(o_v.ptr(), k, ogsType<T>::get()); }
 };
 
 }  // namespace ogs

@@ -204,7 +204,7 @@ void ogs_t::GatherScatterFinish(void* o_v, int k, Type type, Op op, Transpose tr
   SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
   spn_stream_t cur = platform.getStream();
   spn_stream_t hs = (NhaloT == 0 && comm.size() == 1) ? cur : ForkHalo();  // halo chain: its own stream, next to the interior operator
-  if (!(g_debug_skip & 2)) gatherLocal->GatherScatter(o_v, k, type, op, trans, cur);  // interior rows
+  if (!(g_debug_skip & 2) && !halo_only) gatherLocal->GatherScatter(o_v, k, type, op, trans, cur);  // interior rows
   if (NhaloT == 0 && comm.size() == 1) return;
   if (g_debug_skip & 4) { peer_exchange_in_flight = false; FinishExchange(); JoinHalo(); return; }
   const ogsExchangeData_t& d = data[trans];
@@ -272,6 +272,26 @@ void ogs_t::HostGatherScatterFinish(void* h_v) {
   }
   SPN_ABORT("HostGatherScatterFinish: no operation in flight on this host vector", true);
 }
+
+// ---------------------------------------------------------------------------------------------
+// halo_t (libs/ogs/ogsHalo.cpp:39-400, device-buffer versions).  In the reference
+//   Exchange = gatherHalo->Gather(NoTrans) -> exchange(NoTrans) -> gatherHalo->Scatter(NoTrans)
+//   Combine  = gatherHalo->Gather(Trans)   -> exchange(Trans)   -> gatherHalo->Scatter(Trans)
+// i.e. the halo half of GatherScatter(Add, NoTrans / Trans) with no interior operator — which is what an ogs_t
+// set up with Kind Halo runs (halo_only).
+// ---------------------------------------------------------------------------------------------
+void halo_t::Setup(const dlong N, hlong* ids, comm_t comm, const Method method, const bool verbose, platform_t& platform) {
+  ogs.Setup(N, ids, comm, Halo, method, /*unique=*/false, verbose, platform);
+  Nhalo = ogs.NhaloT - ogs.NhaloP;  // halo_t::Setup, libs/ogs/ogsSetup.cpp:81
+}
+void halo_t::SetupHost(const dlong N, hlong* ids, comm_t comm, const bool verbose) {
+  ogs.SetupHost(N, ids, comm, Halo, /*unique=*/false, verbose);
+  Nhalo = ogs.NhaloT - ogs.NhaloP;
+}
+void halo_t::ExchangeStart(void* o_v, int k, Type type) { ogs.GatherScatterStart(o_v, k, type, Add, NoTrans); }
+void halo_t::ExchangeFinish(void* o_v, int k, Type type) { ogs.GatherScatterFinish(o_v, k, type, Add, NoTrans); }
+void halo_t::CombineStart(void* o_v, int k, Type type) { ogs.GatherScatterStart(o_v, k, type, Add, Trans); }
+void halo_t::CombineFinish(void* o_v, int k, Type type) { ogs.GatherScatterFinish(o_v, k, type, Add, Trans); }
 
 // ---------------------------------------------------------------------------------------------
 // Gather (libs/ogs/ogs.cpp:206-301): o_gv = [NlocalT local rows | NhaloP owned halo rows]

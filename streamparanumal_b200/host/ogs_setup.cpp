@@ -171,6 +171,7 @@ void ogs_t::Free() {
   NgatherGlobal = 0;
   on_device = false;
   exchange_in_flight = false;
+  halo_only = false;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -282,6 +283,7 @@ const void* ogs_t::PeerWaitTable(spn_p2p_wait_t& w, int mode) const {
 }
 
 void ogs_t::AssertGatherDefined() const {
+  SPN_ABORT("Gather / Scatter are not operations of a halo_t (Kind Halo): use Exchange / Combine", halo_only);
   SPN_ABORT("Gather operation not well-defined.", !gather_defined);  // libs/ogs/ogsSetup.cpp:827-830
 }
 
@@ -298,7 +300,7 @@ void ogs_t::Setup(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_, co
   SetupPlan(N_, ids, comm_, kind_, unique_, verbose);
 
   // device copies (reference: ogsOperator_t ctor uploads, libs/ogs/ogsOperator.cpp:618-665)
-  gatherLocal->upload(platform, /*tile_plans=*/true);
+  if (!halo_only) gatherLocal->upload(platform, /*tile_plans=*/true);  // a halo_t never touches its local rows
   gatherHalo->upload(platform, /*tile_plans=*/false);
   for (int m = 0; m < 3; ++m) {
     ogsExchangeData_t& d = data[m];
@@ -356,7 +358,9 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   const int rank = comm.rank(), size = comm.size();
 
   SPN_ABORT("Invalid ogs setup requested", (kind == Unsigned && unique) || (kind == Halo && unique));
-  SPN_ABORT("halo_t (Kind Halo) is outside the hot path and not provided", kind == Halo);
+  // Kind Halo (halo_t::Setup, libs/ogs/ogsSetup.cpp:73-82): a Signed, non-unique operator of which only the rows
+  // shared between ranks act — the reference builds no gatherLocal for it (ogsSetup.cpp:592-603)
+  halo_only = (kind == Halo);
 
   // ---- non-zero labels, in column order ----------------------------------------------------
   dlong Nids = 0;
@@ -447,6 +451,8 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
 
   comm.Allreduce(is_unique, Comm::Min);
   gather_defined = (is_unique == 1);
+  // libs/ogs/ogsSetup.cpp:405-408
+  SPN_ABORT("Halo exchange not well-defined. Some baseId groups have no unique positive id.", kind == Halo && !gather_defined);
   if (verbose) {
     hlong total = NsharedLabels;
     comm.Allreduce(total);

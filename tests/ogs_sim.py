@@ -73,7 +73,7 @@ def gather_scatter(plan, v, K=1, op=0, trans=host.SYM):
     send = pyoracle.ogs_extract(d["sendIds"], own, K=K) if d["Nsend"] else np.zeros(0, dtype=v.dtype)
     recv = exchange(d, send, K)
     out = v.copy()
-    if o.NlocalT:
+    if o.NlocalT and getattr(o, "kind", host.SIGNED) != host.HALO:  # a halo_t has no interior operator
         out = pyoracle.ogs_gather_scatter(*plan.local[g], *plan.local[s], out, K=K, op=op)
     if o.NhaloT:
         folded = combine(d, own, recv, K, op)

@@ -241,3 +241,53 @@ def test_multirank_ogs_t_nccl(world, nx, ny, nz, p, K, dtype, kind_unique, excha
         pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")
     with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
         mp.spawn(_worker, args=(world, _free_port(), tmpdir, nx, ny, nz, p, K, dtype, kind_unique, exchange), nprocs=world, join=True)
+
+
+# ---------------------------------------------------------------------------------------------- halo_t on devices
+def _halo_worker(rank, world, port, tmpdir, K, dtype_name, exchange):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["LOCAL_RANK"] = str(rank)
+    os.environ["SPN_OGS_EXCHANGE"] = exchange
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ogs_sim
+        import test_halo_cpu
+        from streamparanumal_b200 import host
+        torch.cuda.set_device(rank)
+        dev = f"cuda:{rank}"
+        comm = host.Comm(rank, world, rendezvous=tmpdir)
+        platform = host.Platform(comm, rank)
+        ids = test_halo_cpu._ids(rank, world)
+        halo = host.Ogs(ids.copy(), comm, kind=host.HALO, unique=False, platform=platform)
+        plan = ogs_sim.Plan(halo)
+        v = _values(ids.size * K, NP_OF[dtype_name], 600 + rank)
+        for _ in range(3):  # repeated calls: both receive halves of the peer-memory exchange get used
+            d_v = torch.from_numpy(v.copy()).to(dev)
+            halo.HaloExchange(d_v, K)
+            assert np.array_equal(d_v.cpu().numpy(), ogs_sim.gather_scatter(plan, v, K=K, op=host.ADD, trans=host.NOTRANS)), "Exchange"
+            d_v = torch.from_numpy(v.copy()).to(dev)
+            halo.HaloCombine(d_v, K)
+            assert np.array_equal(d_v.cpu().numpy(), ogs_sim.gather_scatter(plan, v, K=K, op=host.ADD, trans=host.TRANS)), "Combine"
+        with pytest.raises(RuntimeError):
+            halo.Gather(torch.zeros(8, device=dev, dtype=torch.float64), torch.zeros(ids.size, device=dev, dtype=torch.float64))
+        torch.cuda.synchronize()
+        dist.barrier()
+        halo.close()
+        platform.close()
+        comm.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("world,K,dtype", [(2, 1, "float64"), (3, 2, "int32")])
+def test_multirank_halo_t(world, K, dtype, exchange):
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")
+    with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
+        mp.spawn(_halo_worker, args=(world, _free_port(), tmpdir, K, dtype, exchange), nprocs=world, join=True)
