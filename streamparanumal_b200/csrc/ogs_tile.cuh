@@ -101,16 +101,7 @@ __device__ __forceinline__ T shfl_idx(T x, int src) { return __shfl_sync(0xfffff
 // keeps in flight (measured: 2539 -> 4877 GB/s on BS8, profiles/round1_notes.md).
 template <typename T>
 __device__ __forceinline__ T ld_once(const T* p) { return *p; }
-#ifdef SPN_GS_LD_NA
-// sweep variant: 8-byte value loads that do not allocate in L1 (non-volatile, no memory clobber: a tile's loads are
-// ordered before its own stores by data dependence and other tiles own other columns)
-template <>
-__device__ __forceinline__ double ld_once<double>(const double* p) {
-  double r;
-  asm("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
-  return r;
-}
-#endif
+
 __device__ __forceinline__ unsigned ld_ids(const unsigned* p) {
   unsigned r;
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
@@ -359,8 +350,7 @@ ogs_tile_pf_kernel(int NTall, int chunkTiles, const unsigned* __restrict__ colP,
       acc[u] = OgsOp<T, OP>::init();
       OgsOp<T, OP>::apply(acc[u], xc[u]);
     }
-    // (VAR 8 / 16: timing probes that force 0 / 7 rounds — results are then wrong)
-    const int R = (VAR & 8) ? 0 : (VAR & 16) ? 7 : __reduce_max_sync(0xffffffffu, maxpos);
+    const int R = __reduce_max_sync(0xffffffffu, maxpos);
     if constexpr (sizeof(T) == 8 && OP == SPN_ADD && !std::is_integral<T>::value) {
       double xeff[U];  // own value, or +0.0 on a row head
       int delta[U];    // 1, or 0 on a row head
@@ -392,11 +382,7 @@ ogs_tile_pf_kernel(int NTall, int chunkTiles, const unsigned* __restrict__ colP,
       } else {
         const int lastlane = lane + __ffs(last[u] >> lane) - 1;
         const T total = shfl_idx(acc[u], lastlane & 31);
-#ifdef SPN_GS_PLAIN_ST
-        if (valid) out[col_of<true>(wc[u])] = total;
-#else
         if (valid) __stcs(out + col_of<true>(wc[u]), total);
-#endif
       }
     }
 
