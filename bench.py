@@ -316,7 +316,15 @@ def run_b200(args):
         sampler.start()
         time.sleep(0.3)
     t_step = timed(step, args.steps, 0)
+    # K steps last only ~25 ms, shorter than one nvidia-smi sampling period: keep the same step loop running (untimed) for
+    # about 1.5 s so that the clock / throttle samples are taken under the load of the measured kernel
+    n_load = max(args.steps, int(1.5 / max(t_step, 1e-6)))
+    for _ in range(n_load):
+        step()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["sampled_over"] = f"the timed region ({args.steps} steps) + {n_load} more untimed steps of the same loop"
 
     # ---- e2e: host buffers through the host-buffer call of the host layer (ogs_t::GatherScatterStart/Finish on pinned
     #      host vectors: every step copies its q host->device, runs ogs_t::GatherScatter and copies the result back).
