@@ -50,6 +50,7 @@ const char* spn_error_string(int status) {
     case SPN_ERR_ROW_TOO_LONG: return "spn: row block exceeds spn_ogs_nodes_per_block()";
     case SPN_ERR_NCCL: return "spn: NCCL error";
     case SPN_ERR_NO_DEVICE: return "spn: no CUDA device available (there is no CPU fallback)";
+    case SPN_ERR_OUT_OF_MEMORY: return "spn: out of host or device memory";
     default: break;
   }
   if (status > 0) return cudaGetErrorString((cudaError_t)status);
