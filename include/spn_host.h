@@ -88,7 +88,8 @@ int spn_host_halo_combine(spn_host_ogs_t halo, void* d_v, int k, int type);
 int spn_host_halo_combine_start(spn_host_ogs_t halo, void* d_v, int k, int type);
 int spn_host_halo_combine_finish(spn_host_ogs_t halo, void* d_v, int k, int type);
 
-/* timing probes (key 0: bit mask of ogs_t::GatherScatter phases to skip); not part of the drop-in surface */
+/* key 1: order of a label's copies for the positive pick of ogs_t::Setup (0 stable, 1 the serial reference build's std::sort order);
+ * key 0 (builds with -DSPN_TIMING_PROBES only): bit mask of ogs_t::GatherScatter phases to skip.  Not part of the drop-in surface */
 int spn_host_debug_set(int key, int value);
 
 #ifdef __cplusplus

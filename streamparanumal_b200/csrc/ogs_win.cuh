@@ -23,6 +23,11 @@
 #include <type_traits>
 #include "ogs_tile.cuh"
 
+// timing probes (wrong results): 1 = no far copies, 2 = no stores, 4 = no window copies
+#ifndef SPN_WIN_PROBE
+#define SPN_WIN_PROBE 0
+#endif
+
 namespace spn {
 
 struct OgsWinDesc {  // one per chunk, 16 bytes
@@ -220,7 +225,7 @@ ogs_win_gs_kernel(int NC, const OgsWinDesc* __restrict__ desc, const unsigned sh
       mbar_expect_tx(barMeta + s, (unsigned)St::kIds + farBytes);
       bulk_g2s(ids_of(s), ids16 + c * (TC * 32), St::kIds, barMeta + s);
       if (farBytes) bulk_g2s(far_of(s), farCols + d.farStart, farBytes, barMeta + s);
-      const unsigned winBytes = (unsigned)d.W * (unsigned)sizeof(T);
+      const unsigned winBytes = (SPN_WIN_PROBE & 4) ? 0u : (unsigned)d.W * (unsigned)sizeof(T);
       mbar_expect_tx(barFull + s, winBytes);
       if (winBytes) bulk_g2s(vals_of(s), in + d.c0, winBytes, barFull + s);
       d = dn;
@@ -236,7 +241,9 @@ ogs_win_gs_kernel(int NC, const OgsWinDesc* __restrict__ desc, const unsigned sh
     const int nfar = sdesc[sf].nfar;
     const int* fc = far_of(sf);
     T* fv = vals_of(sf) + WMAX;
+#if !(SPN_WIN_PROBE & 1)
     for (int i = tid; i < nfar; i += NW * 32) cp_async_small<(int)sizeof(T)>(fv + i, in + fc[i]);
+#endif
     cp_async_arrive(barFull + sf);
   };
   int sf = 0;
@@ -314,7 +321,11 @@ ogs_win_gs_kernel(int NC, const OgsWinDesc* __restrict__ desc, const unsigned sh
     for (int u = 0; u < U; ++u) {
       const int lastlane = lane + __ffs(last[u] >> lane) - 1;
       const T total = shfl_idx(acc[u], lastlane & 31);
+#if (SPN_WIN_PROBE & 2)
+      if (slot[u] != kWinEmpty && total == T(12345)) out[col[u]] = total;
+#else
       if (slot[u] != kWinEmpty) out[col[u]] = total;
+#endif
     }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");

@@ -7,7 +7,9 @@
 #include "spn_host.h"
 
 using namespace spn;
+#ifdef SPN_TIMING_PROBES
 namespace spn { namespace ogs { extern int g_debug_skip; } }
+#endif
 
 struct spn_host_comm { comm_t comm; };
 struct spn_host_platform { platform_t platform; };
@@ -189,7 +191,10 @@ int spn_host_ogs_gather_scatter_host_finish(spn_host_ogs_t h, void* h_v) {
   return guarded([&] { h->ogs.HostGatherScatterFinish(h_v); });
 }
 int spn_host_debug_set(int key, int value) {
+#ifdef SPN_TIMING_PROBES
   if (key == 0) { spn::ogs::g_debug_skip = value; return SPN_SUCCESS; }
+#endif
+  if (key == 1) { spn::ogs::SetPositivePickOrder(value); return SPN_SUCCESS; }
   return SPN_ERR_INVALID_ARGUMENT;
 }
 // halo_t operations on an ogs handle set up with kind 2 (Halo): Exchange = owner value to every copy, Combine = every

@@ -35,25 +35,50 @@ void RankDecomp3(int size_x, int size_y, int /*size_z*/, int& rank_x, int& rank_
   rank_z = rank / (size_x * size_y);
 }
 
+// Labels the reference's mesh_t::ConnectNodes converges to (libs/mesh/meshConnectNodes.cpp:44-81): every node starts
+// as 1 + e*Np + n + (nodes of the lower ranks) and repeatedly takes the smaller label of the node across each face, so
+// a node ends with the MINIMUM of that expression over all of its coincident copies, on this rank and on others.
+// For the box that minimum has a closed form: along each axis a lattice coordinate on an element boundary belongs
+// to two elements, so a node has at most 8 copies, enumerated directly.
 void BoxHexGlobalIds(int rank, int size, int nx, int ny, int nz, int p, hlong* ids, hlong* NgatherGlobalExpected) {
   int sx, sy, sz, rx, ry, rz;
   Factor3(size, sx, sy, sz);
   RankDecomp3(sx, sy, sz, rx, ry, rz, rank);
   const int Nq = p + 1, Np = Nq * Nq * Nq;
-  const hlong LX = (hlong)sx * nx * p + 1, LY = (hlong)sy * ny * p + 1, LZ = (hlong)sz * nz * p + 1;
-  if (NgatherGlobalExpected) *NgatherGlobalExpected = LX * LY * LZ;
-  const hlong ox = (hlong)rx * nx * p, oy = (hlong)ry * ny * p, oz = (hlong)rz * nz * p;
+  const hlong NX = (hlong)sx * nx, NY = (hlong)sy * ny, NZ = (hlong)sz * nz;  // global elements per axis
+  if (NgatherGlobalExpected) *NgatherGlobalExpected = (NX * p + 1) * (NY * p + 1) * (NZ * p + 1);
+  const hlong nodesPerRank = (hlong)nx * ny * nz * Np;  // comm.Scan(localNnodes): every rank owns the same count
+  // label of node (i,j,k) of the element at GLOBAL element coordinates (EX,EY,EZ)
+  auto label = [&](hlong EX, hlong EY, hlong EZ, int i, int j, int k) -> hlong {
+    const int qx = (int)(EX / nx), qy = (int)(EY / ny), qz = (int)(EZ / nz);
+    const hlong r = qx + (hlong)qy * sx + (hlong)qz * sx * sy;  // inverse of RankDecomp3 above
+    const hlong e = (EX - (hlong)qx * nx) + (EY - (hlong)qy * ny) * nx + (EZ - (hlong)qz * nz) * nx * ny;
+    return 1 + r * nodesPerRank + e * Np + (i + j * Nq + k * Nq * Nq);
+  };
 #pragma omp parallel for collapse(2)
   for (int ez = 0; ez < nz; ++ez)
     for (int ey = 0; ey < ny; ++ey)
       for (int ex = 0; ex < nx; ++ex) {
         const hlong e = ex + (hlong)ey * nx + (hlong)ez * nx * ny;
+        const hlong EX = (hlong)rx * nx + ex, EY = (hlong)ry * ny + ey, EZ = (hlong)rz * nz + ez;
         hlong* out = ids + e * Np;
         for (int k = 0; k < Nq; ++k)
           for (int j = 0; j < Nq; ++j)
             for (int i = 0; i < Nq; ++i) {
-              const hlong gi = ox + (hlong)ex * p + i, gj = oy + (hlong)ey * p + j, gk = oz + (hlong)ez * p + k;
-              out[i + j * Nq + k * Nq * Nq] = 1 + gi + gj * LX + gk * LX * LY;
+              // the other copy along an axis: node 0 of this element == node p of the previous one, and vice versa
+              const int ax = (i == 0 && EX > 0) ? -1 : (i == p && EX + 1 < NX) ? 1 : 0;
+              const int ay = (j == 0 && EY > 0) ? -1 : (j == p && EY + 1 < NY) ? 1 : 0;
+              const int az = (k == 0 && EZ > 0) ? -1 : (k == p && EZ + 1 < NZ) ? 1 : 0;
+              hlong best = label(EX, EY, EZ, i, j, k);
+              for (int cz = 0; cz <= (az != 0); ++cz)
+                for (int cy = 0; cy <= (ay != 0); ++cy)
+                  for (int cx = 0; cx <= (ax != 0); ++cx) {
+                    if (!(cx | cy | cz)) continue;
+                    const int ii = cx ? (ax < 0 ? p : 0) : i, jj = cy ? (ay < 0 ? p : 0) : j, kk = cz ? (az < 0 ? p : 0) : k;
+                    const hlong v = label(EX + cx * ax, EY + cy * ay, EZ + cz * az, ii, jj, kk);
+                    if (v < best) best = v;
+                  }
+              out[i + j * Nq + k * Nq * Nq] = best;
             }
       }
 }

@@ -22,9 +22,10 @@
 //   * the interior operator runs on the warp-tile plan (csrc/ogs_tile.cuh) when gather CSR == scatter CSR;
 //   * only the Pairwise exchange exists (Method is accepted and ignored): on NVSwitch every peer is
 //     one hop away, which is the case Pairwise is optimal for;
-//   * the positive copy of a label is picked by a hash of the label instead of the reference's
-//     rank-seeded LCG (libs/primitives/random.cpp) — results of every operation are independent of
-//     that choice except which rank stores a shared row of a gathered vector.
+//   * the positive copy of a label is picked by the reference's rule (rank-seeded LCG of libs/primitives/random.cpp,
+//     member  rands[group] % size  of the label group on the directory rank, libs/ogs/ogsSetup.cpp:355-382); the
+//     member ORDER inside a group is implementation-defined in the reference (an unstable sort) — see
+//     SetPositivePickOrder.
 #pragma once
 #include <memory>
 #include <vector>
@@ -51,6 +52,11 @@ template <> struct ogsType<double> { static constexpr Type get() { return Double
 template <> struct ogsType<int> { static constexpr Type get() { return Int32; } };
 template <> struct ogsType<long long int> { static constexpr Type get() { return Int64; } };
 size_t Sizeof(Type type);
+
+// order of the copies of one label on its directory rank, which the positive pick indexes:
+// 0 (default) stable (source rank, position); 1 the order the serial reference build's std::sort leaves them in
+// (exact replica, one more serial sort at setup).  Also SPN_OGS_PICK=stdsort.
+void SetPositivePickOrder(int mode);
 
 // CSR gather operator with its "T" (all copies) and "N" (positive copies only) variants
 // (include/ogs/ogsOperator.hpp:44-138).  Host arrays are always built; upload() makes the device copies.
@@ -264,10 +270,9 @@ class halo_t {
 
 // Box mesh of degree-p hex elements, nx*ny*nz elements per rank on the Factor3(size) process grid
 // (reference: libs/mesh/meshSetupBoxHex3D.cpp:31-131, libs/core/rankDecomp.cpp:55-91,166-213).
-// ids[e*Np+n] is the label of node n=i+j*Nq+k*Nq^2 of local element e=ex+ey*nx+ez*nx*ny: one more than
-// the node's index in the global (NX*p+1)(NY*p+1)(NZ*p+1) lattice, so coincident nodes — on this rank
-// or across ranks — share a label, which is what mesh_t::ConnectNodes converges to
-// (libs/mesh/meshConnectNodes.cpp:44-81) up to the label values themselves.
+// ids[e*Np+n] is the label of node n=i+j*Nq+k*Nq^2 of local element e=ex+ey*nx+ez*nx*ny: the value the reference's
+// mesh_t::ConnectNodes converges to (libs/mesh/meshConnectNodes.cpp:44-81) — the minimum over the node's coincident
+// copies, on any rank, of 1 + e*Np + n + (nodes owned by the lower ranks) — computed in closed form for the box.
 void Factor3(const int n, int& nx, int& ny, int& nz);
 void RankDecomp3(int size_x, int size_y, int size_z, int& rank_x, int& rank_y, int& rank_z, const int rank);
 void BoxHexGlobalIds(int rank, int size, int nx, int ny, int nz, int p, hlong* ids, hlong* NgatherGlobalExpected);

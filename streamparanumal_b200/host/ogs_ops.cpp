@@ -18,8 +18,14 @@ namespace spn {
 namespace ogs {
 
 // timing probe (spn_host_debug_set(0, mask)): 1 skip the halo pack / send, 2 skip the interior operator,
-// 4 skip the halo combine.  Results are wrong with any bit set; used by tools/halo_breakdown.py only.
+// 4 skip the halo combine.  Results are wrong with any bit set, so the probe only exists in builds made with
+// -DSPN_TIMING_PROBES (tools/halo_breakdown.py); the shipped library compiles the checks away.
+#ifdef SPN_TIMING_PROBES
 int g_debug_skip = 0;
+#define SPN_PROBE_SKIP(bit) (g_debug_skip & (bit))
+#else
+#define SPN_PROBE_SKIP(bit) false
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // ogsOperator_t
@@ -179,7 +185,7 @@ void ogs_t::FinishExchange() {
 void ogs_t::GatherScatterStart(void* o_v, int k, Type type, Op op, Transpose trans) {
   SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
   if (NhaloT == 0 && comm.size() == 1) return;
-  if (g_debug_skip & 1) return;
+  if (SPN_PROBE_SKIP(1)) return;
   AllocBuffer((size_t)k * Sizeof(type));
   const ogsExchangeData_t& d = data[trans];
   // halo partials: gather over the T copies unless NoTrans (positive copies only), straight into send order
@@ -204,9 +210,9 @@ void ogs_t::GatherScatterFinish(void* o_v, int k, Type type, Op op, Transpose tr
   SPN_ABORT("ogs_t used before Setup on a platform", !on_device);
   spn_stream_t cur = platform.getStream();
   spn_stream_t hs = (NhaloT == 0 && comm.size() == 1) ? cur : ForkHalo();  // halo chain: its own stream, next to the interior operator
-  if (!(g_debug_skip & 2) && !halo_only) gatherLocal->GatherScatter(o_v, k, type, op, trans, cur);  // interior rows
+  if (!SPN_PROBE_SKIP(2) && !halo_only) gatherLocal->GatherScatter(o_v, k, type, op, trans, cur);  // interior rows
   if (NhaloT == 0 && comm.size() == 1) return;
-  if (g_debug_skip & 4) { peer_exchange_in_flight = false; FinishExchange(); JoinHalo(); return; }
+  if (SPN_PROBE_SKIP(4)) { peer_exchange_in_flight = false; FinishExchange(); JoinHalo(); return; }
   const ogsExchangeData_t& d = data[trans];
   // scatter side: every copy, except Trans which writes positive copies only (ogsOperator.cpp:303-321)
   const bool sN = (trans == Trans);

@@ -10,6 +10,7 @@
 //      receiver agree on the message layout without exchanging row indices (the reference ships
 //      remote row ids through four more alltoallv rounds: ogsSetup.cpp:617-813).
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <numeric>
@@ -39,12 +40,32 @@ namespace {
 
 inline hlong habs(hlong x) { return x < 0 ? -x : x; }
 
-// splitmix64 finaliser: picks the positive copy of a label deterministically
-inline unsigned long long mix64(unsigned long long z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
+// The reference's generator for the positive-copy pick: prim::random<int> after prim::seedRNG(rank)
+// (libs/primitives/random.cpp:45-164, seeded at libs/ogs/ogsSetup.cpp:110-112): the 64-bit LCG
+// X(n+1) = a X(n) + c, first state a * (~0 ^ seed) + c, value n = |int(X(n))|.
+struct RefLcg {
+  unsigned long long x;
+  explicit RefLcg(unsigned long long seed) : x(6364136223846793005ULL * (~0ULL ^ seed) + 1ULL) {}
+  int next() {
+    const int v = static_cast<int>(x);
+    x = 6364136223846793005ULL * x + 1ULL;
+    return v < 0 ? (v == INT_MIN ? v : -v) : v;  // std::abs(int), INT_MIN left as the reference leaves it
+  }
+};
+
+// 0: members of a label group in (source rank, source order) — the stable order, the default;
+// 1: members in the order the reference's own `prim::sort` leaves them in (std::sort on the values only,
+//    libs/primitives/sort.cpp:176-190 built without GLIBCXX_PARALLEL; libs/ogs/ogsSetup.cpp:341-343): an exact replica
+//    of the serial reference build, used to pin the maps against it (costs one more serial sort).
+// The reference's own order is implementation-defined (an unstable sort; thread-count dependent with
+// GLIBCXX_PARALLEL), so both are instances of its rule.  SPN_OGS_PICK=stdsort selects 1.
+int g_pick_mode = -1;
+int pick_mode() {
+  if (g_pick_mode < 0) {
+    const char* e = getenv("SPN_OGS_PICK");
+    g_pick_mode = (e && std::string(e) == "stdsort") ? 1 : 0;
+  }
+  return g_pick_mode;
 }
 
 struct Key {
@@ -142,6 +163,8 @@ std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const std:
 }
 
 }  // namespace
+
+void SetPositivePickOrder(int mode) { g_pick_mode = mode ? 1 : 0; }
 
 void ogs_t::Free() {
   if (packedEvent) { spn_event_destroy(packedEvent); packedEvent = nullptr; }
@@ -403,6 +426,17 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
     return (int)(std::upper_bound(recvOffsets.begin(), recvOffsets.end(), (int)idx) - recvOffsets.begin()) - 1;
   };
 
+  // positive-copy pick of the reference (libs/ogs/ogsSetup.cpp:355-382): group n of this directory rank, in ascending
+  // label order, takes member  rands[n] % (group size)  with rands from the rank-seeded LCG
+  RefLcg lcg((unsigned long long)rank);
+  std::vector<std::pair<hlong, dlong>> refOrder;  // pick mode 1: (|label|, receive slot) as std::sort leaves them
+  if (unique && pick_mode() == 1) {
+    refOrder.resize((size_t)recvN);
+    for (dlong i = 0; i < recvN; ++i) refOrder[i] = {habs(recvLabels[i]), i};
+    std::sort(refOrder.begin(), refOrder.end(),
+              [](const std::pair<hlong, dlong>& a, const std::pair<hlong, dlong>& b) { return a.first < b.first; });
+  }
+
   std::vector<int> recvShared((size_t)recvN, 0);
   std::vector<std::vector<hlong>> reply(size);  // per source rank: [label, nranks, (rank*2+positive)...] per shared label
   int is_unique = 1;
@@ -414,10 +448,11 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
       while (e < recvN && keys[e].label == keys[s].label) ++e;
       const hlong label = keys[s].label;
       if (unique) {
-        // one positive copy per label (reference: random pick, libs/ogs/ogsSetup.cpp:364-382)
-        const dlong m = (dlong)(mix64((unsigned long long)label) % (unsigned long long)(e - s));
+        // one positive copy per label (libs/ogs/ogsSetup.cpp:364-382)
+        const int m = lcg.next() % (int)(e - s);
         for (dlong i = s; i < e; ++i) recvLabels[keys[i].idx] = -label;
-        recvLabels[keys[s + m].idx] = label;
+        const dlong picked = refOrder.empty() ? keys[s + m].idx : refOrder[(size_t)(s + m)].second;
+        recvLabels[picked] = label;
       } else {
         int positives = 0;
         for (dlong i = s; i < e; ++i) positives += (recvLabels[keys[i].idx] > 0) ? 1 : 0;

@@ -7,6 +7,8 @@ second), all-ones -> node multiplicity, Scatter o Gather == GatherScatter, sum c
   C2  BS1-BS4 at the top of the sweep, 4 GiB moved          (BS/BS1..4/src/bs*Run.cpp)
   C3/C4  BS6 / BS7 / BS8 on the 64^3 degree-7 hex box through ogs_t (BS/BS6..8/src/bs*Run.cpp)
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -118,6 +120,20 @@ def test_c3_c4_ogs_full_size_properties():
         ogs.Scatter(s, g, 1, host.NOTRANS)
         ogs.GatherScatter(xr, 1, host.ADD, host.SYM)
         assert torch.equal(s, xr)
+        # ... and against the CPU oracle on the plan's own CSR at the FULL size (the oracle walks 2^27 non-zeros in
+        # about a second per call with the host threads): BS6, BS7 and BS8 bit for bit
+        from oracle import pyoracle
+        ci = ogs.array("local_colIdsT")
+        threads = os.cpu_count() or 1
+        x0 = util.splitmix64(n, 43)
+        assert np.array_equal(xr.cpu().numpy().view(np.int64),
+                              pyoracle.ogs_gather_scatter(rs, ci, rs, ci, x0, threads=threads).view(np.int64))   # BS8
+        assert np.array_equal(g.cpu().numpy().view(np.int64), pyoracle.ogs_gather(rs, ci, x0, threads=threads).view(np.int64))  # BS6
+        gq = util.splitmix64(ogs.Ngather, 44)
+        d_gq = torch.from_numpy(gq).cuda()
+        ogs.Scatter(s, d_gq, 1, host.NOTRANS)
+        assert np.array_equal(s.cpu().numpy().view(np.int64),
+                              pyoracle.ogs_scatter(rs, ci, gq, np.zeros(n), threads=threads).view(np.int64))      # BS7
     finally:
         ogs.close()
         platform.close()

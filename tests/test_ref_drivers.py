@@ -1,0 +1,98 @@
+"""The reference's own sources behind the drop-in boundary.
+
+build/ref_drivers/BS0..BS8 are the reference's BS drivers, libs/core, libs/primitives, libs/ogs and libs/mesh compiled
+UNCHANGED from /root/reference against include/shim/{occa.hpp,mpi.h} and linked with the product backend of the OCCA shim
+(streamparanumal_b200/shim/occa_spn.cpp -> C ABI -> sm_100a kernels): platform_t::buildKernel, kernel_t::operator(),
+deviceMemory<T>, device.finish / setStream — every call site of SURVEY.md section 8(b) — run as written
+(`make ref-drivers`; the binaries travel to the GPU box, /root/reference does not).
+oracle/_ref/BS0..BS8 are the same sources with the HOST backend (test infrastructure): the reference's `-m Serial` path.
+CPU: the binaries exist, keep the reference CLI and refuse anything but CUDA.  GPU: every driver runs on the B200 and
+prints the reference's line; BS5 at the BASELINE size; DOF counts equal those of the reference's Serial executables."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRV = os.path.join(ROOT, "build", "ref_drivers")
+SERIAL = os.path.join(ROOT, "oracle", "_ref")
+NUM = r"[-+0-9.eE]+"
+HAVE_REF = os.path.isdir("/root/reference/BS")
+
+
+def run(args, timeout=600):
+    return subprocess.run(args, capture_output=True, text=True, timeout=timeout)
+
+
+def need(path):
+    if not os.access(path, os.X_OK):
+        if HAVE_REF:
+            pytest.fail(f"{path} missing although /root/reference is here: run `make ref-drivers` / `make -C oracle`")
+        pytest.skip(f"{path} not built (it is compiled where /root/reference exists)")
+    return path
+
+
+def test_reference_sources_compile_against_the_shims():
+    for n in range(9):
+        need(os.path.join(DRV, f"BS{n}"))
+
+
+def test_reference_cli_unchanged_and_no_cpu_mode():
+    exe = need(os.path.join(DRV, "BS5"))
+    r = run([exe, "--help"])  # (the reference exits with LIBP_ERROR after printing its usage: libs/core/settings.cpp)
+    for flag in ("-m", "--mode", "-b", "--bytes", "-bmin", "-bmax", "-s", "--bstep", "-v", "-d", "-pl"):
+        assert flag in r.stdout
+    r = run([exe, "-m", "Serial", "-b", "4096"])       # the product backend implements CUDA only
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    r = run([need(os.path.join(DRV, "BS8")), "--help"])
+    for flag in ("-e", "--elements", "-nx", "-ny", "-nz", "-p", "--degree"):
+        assert flag in r.stdout
+
+
+def test_reference_serial_executables_run_on_the_cpu():
+    """oracle/_ref/BSn -m Serial: the reference's CPU path (host code + its own OKL kernels), the CPU arm of bench.py"""
+    r = run([need(os.path.join(SERIAL, "BS5")), "-m", "Serial", "-b", str(24 * 100000)])
+    assert r.returncode == 0, r.stderr
+    m = re.search(rf"BS5 = \[(\d+) ({NUM}) ({NUM}) +({NUM})\]; %CG Update", r.stdout)
+    assert m and int(m.group(1)) == 100000
+    r = run([need(os.path.join(SERIAL, "BS8")), "-m", "Serial", "-nx", "3", "-ny", "2", "-nz", "2", "-p", "5"])
+    assert r.returncode == 0, r.stderr
+    m = re.search(rf"BS8 = \[(\d+), (\d+), ({NUM}), ({NUM}), +({NUM}), +({NUM})\]; % GatherScatter", r.stdout)
+    assert m and int(m.group(1)) == 5 and int(m.group(2)) == 16 * 11 * 11
+
+
+@pytest.mark.gpu
+def test_reference_bs5_runs_on_the_b200_at_the_baseline_size():
+    r = run([need(os.path.join(DRV, "BS5")), "-b", "1610612736"])   # N = 2^26 (BASELINE.json configs[0])
+    assert r.returncode == 0, r.stderr
+    m = re.fullmatch(rf"BS5 = \[(\d+) ({NUM}) ({NUM}) +({NUM})\]; %CG Update \[DOFs, elapsed, DOFs/s, BW \(GB/s\)\]\n", r.stdout)
+    assert m, r.stdout
+    assert int(m.group(1)) == 1 << 26
+    assert float(m.group(4)) > 3000.0, f"BS5 through the reference driver: {m.group(4)} GB/s"
+
+
+@pytest.mark.gpu
+def test_every_reference_driver_runs_on_the_b200():
+    titles = {1: "Copy", 2: "AXPY", 3: "Norm", 4: "Dot", 5: "CG Update"}
+    per_entry = {1: 16, 2: 24, 3: 8, 4: 16, 5: 24}
+    for n, title in titles.items():
+        r = run([need(os.path.join(DRV, f"BS{n}")), "-b", str(48 << 20)])
+        assert r.returncode == 0, r.stderr
+        m = re.fullmatch(rf"BS{n} = \[(\d+) ({NUM}) ({NUM}) +({NUM})\]; %{title} \[DOFs, elapsed, DOFs/s, BW \(GB/s\)\]\n", r.stdout)
+        assert m, r.stdout
+        assert int(m.group(1)) == (48 << 20) // per_entry
+    r = run([need(os.path.join(DRV, "BS0")), "-n", "100"])
+    assert r.returncode == 0 and re.search(r"BS0 = \[100 ", r.stdout), r.stdout + r.stderr
+    # the ogs drivers: the reference's mesh_t + ogs_t::Setup + ogsOperator_t on the device kernels; DOFs must equal what the
+    # reference's Serial executable reports for the same mesh
+    for n, title in ((6, "Gather"), (7, "Scatter"), (8, "GatherScatter")):
+        args = ["-nx", "6", "-ny", "5", "-nz", "4", "-p", "7"]
+        r = run([need(os.path.join(DRV, f"BS{n}"))] + args)
+        assert r.returncode == 0, r.stderr
+        m = re.search(rf"BS{n} = \[(\d+), (\d+), ({NUM}), ({NUM}), +({NUM}), +({NUM})\]; % {title} ", r.stdout)
+        assert m, r.stdout
+        assert int(m.group(1)) == 7 and int(m.group(2)) == 43 * 36 * 29
+        s = run([need(os.path.join(SERIAL, f"BS{n}")), "-m", "Serial"] + args)
+        ms = re.search(rf"BS{n} = \[(\d+), (\d+),", s.stdout)
+        assert ms and ms.group(2) == m.group(2)
