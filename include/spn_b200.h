@@ -191,18 +191,13 @@ int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h
                         const int* d_rowStarts, const int* d_colIds);
 int spn_ogs_plan_destroy(spn_ogs_plan_t plan);
 int spn_ogs_plan_info(spn_ogs_plan_t plan, int* Ntiles, int* Nirregular, size_t* plan_bytes);
-/* window form used by the K == 1 gather+scatter (csrc/ogs_win.cuh): chunks, columns outside their chunk's window,
- * columns the windows cover (>= Ncols where windows overlap), largest far list of a chunk; Nchunks == 0: the operator
- * does not fit the window form (some chunk has more far columns than a stage holds) and runs on the warp tiles */
-int spn_ogs_plan_window_info(spn_ogs_plan_t plan, int* Nchunks, long long* NfarColumns, long long* NwindowColumns, int* maxFar);
 int spn_ogs_plan_gather(spn_ogs_plan_t plan, int K, const void* v, void* gv, int type, int op, spn_stream_t stream);
 int spn_ogs_plan_scatter(spn_ogs_plan_t plan, int K, const void* gv, void* v, int type, spn_stream_t stream);
 int spn_ogs_plan_gather_scatter(spn_ogs_plan_t plan, int K, void* v, int type, int op, spn_stream_t stream);
 /* out-of-place form: w[col] = OP_{col' in row(col)} v[col'] for every column of the operator
  * (entries of w outside the operator are left untouched) */
 int spn_ogs_plan_gather_scatter_to(spn_ogs_plan_t plan, int K, const void* v, void* w, int type, int op, spn_stream_t stream);
-/* tuning/experiment knobs (key 4 / 5: iterations per CTA of the gather+scatter / gather tile kernel, 0 = persistent;
- * key 6: 0 = K == 1 gather+scatter on the warp tiles instead of the window-staged kernel);
+/* tuning/experiment knobs (key 4 / 5: iterations per CTA of the gather+scatter / gather tile kernel, 0 = persistent);
  * not part of the drop-in surface */
 int spn_debug_set(int key, int value);
 

@@ -72,7 +72,6 @@ KERNEL_SIGNATURES = {
     "spn_ogs_plan_create": [POINTER(c_void_p), c_int, c_int, _IP, _IP, _IP, _IP],
     "spn_ogs_plan_destroy": [_P],
     "spn_ogs_plan_info": [_P, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)],
-    "spn_ogs_plan_window_info": [_P, POINTER(c_int), POINTER(ctypes.c_longlong), POINTER(ctypes.c_longlong), POINTER(c_int)],
     "spn_ogs_plan_gather": [_P, c_int, _P, _P, c_int, c_int, _P],
     "spn_ogs_plan_scatter": [_P, c_int, _P, _P, c_int, _P],
     "spn_ogs_plan_gather_scatter": [_P, c_int, _P, c_int, c_int, _P],

@@ -6,7 +6,6 @@
 #include <new>
 #include <vector>
 #include "ogs_tile.cuh"
-#include "ogs_win.cuh"
 
 // Launch geometry per operation, from the sweeps in profiles/r01_notes.md (B200, degree-7 hex; gather+scatter re-swept
 // after the instruction diet of the fold: U=4 with four resident CTAs beats U=8 with two, 0.487 vs 0.517 ms):
@@ -48,29 +47,6 @@
 #define SPN_TILE_CTAS_GS (SPN_TILE_MINB_GS * 256 / 128)
 #endif
 
-// Window-staged gather+scatter (ogs_win.cuh): tiles per chunk, window columns, pipeline stages, CTA size, CTAs per SM
-#ifndef SPN_WIN_TC
-#define SPN_WIN_TC 32
-#endif
-#ifndef SPN_WIN_WMAX
-#define SPN_WIN_WMAX 1536
-#endif
-#ifndef SPN_WIN_FMAX
-#define SPN_WIN_FMAX 384
-#endif
-#ifndef SPN_WIN_S
-#define SPN_WIN_S 5
-#endif
-#ifndef SPN_WIN_L
-#define SPN_WIN_L (SPN_WIN_S - 2)
-#endif
-#ifndef SPN_WIN_NW
-#define SPN_WIN_NW 8
-#endif
-#ifndef SPN_WIN_MINB
-#define SPN_WIN_MINB 2
-#endif
-
 template <int MODE> struct TileGeom;
 template <> struct TileGeom<spn::TILE_GATHER> { static constexpr int U = SPN_TILE_U_G, MINB = SPN_TILE_MINB_G, PF_TH = SPN_TILE_TH_G, PF_MINB = SPN_TILE_CTAS_G; };
 template <> struct TileGeom<spn::TILE_SCATTER> { static constexpr int U = SPN_TILE_U_S, MINB = SPN_TILE_MINB_S, PF_TH = SPN_TILE_THREADS, PF_MINB = SPN_TILE_MINB_S; };
@@ -90,15 +66,6 @@ struct spn_ogs_plan {
   long long Ncols;
   const int* d_rowStarts;  // borrowed
   const int* d_colIds;     // borrowed
-  // window form of the tiles for K == 1 gather+scatter (ogs_win.cuh); all owned
-  int NC;                    // chunks of SPN_WIN_TC tiles
-  spn::OgsWinDesc* d_wdesc;  // [NC]
-  unsigned short* d_ids16;   // [NC * TC * 32] shared-memory slot per non-zero
-  int* d_farCols;            // far column lists, one per chunk (padded to multiples of 4)
-  long long nfarTotal;       // padded far entries
-  long long nfar;            // far entries
-  long long winCols;         // sum of the window lengths
-  int maxFar;                // largest far list of a chunk
 };
 
 namespace {
@@ -120,31 +87,6 @@ int resident_ctas(K kern, int threads, int* cache) {
   return SPN_SUCCESS;
 }
 
-// K == 1 gather+scatter through the window-staged kernel (spn_debug_set key 6: 0 = warp tiles only)
-int g_use_win = 0;  // off until it beats the warp tiles (profiles/r02_notes.md)
-
-template <typename T, int OP>
-int launch_win(const spn_ogs_plan* p, DeviceInfo* d, const void* in, void* out, cudaStream_t st) {
-  constexpr int TC = SPN_WIN_TC, WMAX = SPN_WIN_WMAX, FMAX = SPN_WIN_FMAX, S = SPN_WIN_S, NW = SPN_WIN_NW, MB = SPN_WIN_MINB;
-  constexpr int TH = (NW + 1) * 32;
-  constexpr int smem = ogs_win_smem_bytes<T, TC, WMAX, FMAX, S>();
-  auto kern = ogs_win_gs_kernel<T, OP, TC, WMAX, FMAX, S, SPN_WIN_L, NW, MB>;
-  // opt-in to > 48 KB of dynamic shared memory and the resident CTA count, once per device
-  static int res[64] = {0};
-  const int dev = d->device & 63;
-  if (!res[dev]) {
-    SPN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int per_sm = 0;
-    SPN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TH, smem));
-    if (per_sm < 1) return SPN_ERR_UNSUPPORTED;
-    res[dev] = per_sm;
-  }
-  const int grid = std::min(p->NC, res[dev] * d->sms);
-  kern<<<grid, TH, smem, st>>>(p->NC, p->d_wdesc, p->d_ids16, p->d_farCols, static_cast<const T*>(in), static_cast<T*>(out));
-  SPN_LAUNCH_CHECK();
-  return SPN_SUCCESS;
-}
-
 template <typename T, int OP, int MODE>
 int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaStream_t st) {
   DeviceInfo* d;
@@ -156,11 +98,7 @@ int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaSt
     constexpr int U = TileGeom<MODE>::U, TH = SPN_TILE_THREADS, MB = TileGeom<MODE>::MINB;
     const int warps_needed = (NT + U - 1) / U;
     const int ctas_needed = (warps_needed + TH / 32 - 1) / (TH / 32);
-    const bool aligned32 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
-    if (K == 1 && MODE == TILE_GATHER_SCATTER && g_use_win && p->NC > 0 && aligned32) {
-      rc = launch_win<T, OP>(p, d, in, out, st);
-      if (rc) return rc;
-    } else if (K == 1 && MODE != TILE_SCATTER) {
+    if (K == 1 && MODE != TILE_SCATTER) {
       constexpr int M2 = (MODE == TILE_SCATTER) ? TILE_GATHER : MODE;  // (scatter never reaches this kernel)
       constexpr int PTH = TileGeom<MODE>::PF_TH, PMB = TileGeom<MODE>::PF_MINB;
       auto kern = ogs_tile_pf_kernel<T, OP, M2, U, PTH, PMB>;
@@ -223,45 +161,6 @@ int dispatch_type(const spn_ogs_plan* p, int K, const void* in, void* out, int t
 
 extern "C" {
 
-// build of the window form from the packed tiles (device passes + one host scan of the far counts)
-static int build_window_plan(spn_ogs_plan* p) {
-  constexpr int TC = SPN_WIN_TC, WMAX = SPN_WIN_WMAX;
-  p->NC = (p->NT + TC - 1) / TC;
-  if (p->NC == 0 || p->Ncols <= 0) { p->NC = 0; return SPN_SUCCESS; }
-  const size_t NC = (size_t)p->NC;
-  SPN_CUDA_TRY(cudaMalloc(&p->d_wdesc, sizeof(OgsWinDesc) * NC));
-  ogs_win_count_kernel<TC, WMAX><<<(unsigned)((NC * 32 + 255) / 256), 256>>>(p->NC, p->NT, (int)p->Ncols, p->d_colP, p->d_wdesc);
-  SPN_LAUNCH_CHECK();
-  std::vector<OgsWinDesc> desc(NC);
-  SPN_CUDA_TRY(cudaMemcpy(desc.data(), p->d_wdesc, sizeof(OgsWinDesc) * NC, cudaMemcpyDeviceToHost));
-  long long total = 0;
-  int maxfar = 0;
-  for (size_t c = 0; c < NC; ++c) maxfar = std::max(maxfar, desc[c].nfar);
-  p->maxFar = maxfar;
-  if (maxfar > SPN_WIN_FMAX) {
-    // some chunk scatters more columns than a stage holds: this operator stays on the warp tiles
-    cudaFree(p->d_wdesc);
-    p->d_wdesc = nullptr;
-    p->NC = 0;
-    return SPN_SUCCESS;
-  }
-  for (size_t c = 0; c < NC; ++c) {
-    p->nfar += desc[c].nfar;
-    p->winCols += desc[c].W;
-    desc[c].farStart = (int)total;
-    total += (desc[c].nfar + 3) & ~3;
-    if (total > 0x7fffffffLL) return SPN_ERR_INVALID_ARGUMENT;
-  }
-  p->nfarTotal = total;
-  SPN_CUDA_TRY(cudaMemcpy(p->d_wdesc, desc.data(), sizeof(OgsWinDesc) * NC, cudaMemcpyHostToDevice));
-  SPN_CUDA_TRY(cudaMalloc(&p->d_ids16, sizeof(unsigned short) * 32 * TC * NC));
-  SPN_CUDA_TRY(cudaMalloc(&p->d_farCols, sizeof(int) * (size_t)std::max<long long>(total, 4)));
-  ogs_win_fill_kernel<TC, WMAX><<<(unsigned)((NC * 32 + 255) / 256), 256>>>(p->NC, p->NT, p->d_colP, p->d_wdesc, p->d_ids16, p->d_farCols);
-  SPN_LAUNCH_CHECK();
-  SPN_CUDA_TRY(cudaDeviceSynchronize());
-  return SPN_SUCCESS;
-}
-
 static int status_of_cuda(int rc) { return rc == (int)cudaErrorMemoryAllocation ? SPN_ERR_OUT_OF_MEMORY : rc; }
 
 // device side of spn_ogs_plan_create; on failure the caller destroys whatever was allocated
@@ -297,7 +196,7 @@ static int build_device_plan(spn_ogs_plan* p, const std::vector<OgsTileDesc>& ti
     }
     SPN_CUDA_TRY(cudaDeviceSynchronize());
   }
-  return build_window_plan(p);
+  return SPN_SUCCESS;
 }
 
 int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h_rowStarts, const int* h_colIds,
@@ -373,9 +272,6 @@ int spn_ogs_plan_destroy(spn_ogs_plan_t plan) {
   if (plan->d_row0) cudaFree(plan->d_row0);
   if (plan->d_rowOf) cudaFree(plan->d_rowOf);
   if (plan->d_irr) cudaFree(plan->d_irr);
-  if (plan->d_wdesc) cudaFree(plan->d_wdesc);
-  if (plan->d_ids16) cudaFree(plan->d_ids16);
-  if (plan->d_farCols) cudaFree(plan->d_farCols);
   delete plan;
   return SPN_SUCCESS;
 }
@@ -386,18 +282,7 @@ int spn_ogs_plan_info(spn_ogs_plan_t plan, int* Ntiles, int* Nirregular, size_t*
   if (Nirregular) *Nirregular = plan->nIrr;
   if (plan_bytes)
     *plan_bytes = (sizeof(unsigned) * 32 + sizeof(int)) * (size_t)(plan->NT + kTilePad) + sizeof(int) * (size_t)plan->nIrr +
-                  sizeof(int) * (size_t)plan->Ncols +
-                  (size_t)plan->NC * (sizeof(spn::OgsWinDesc) + sizeof(unsigned short) * 32 * SPN_WIN_TC) +
-                  sizeof(int) * (size_t)plan->nfarTotal;
-  return SPN_SUCCESS;
-}
-
-int spn_ogs_plan_window_info(spn_ogs_plan_t plan, int* Nchunks, long long* NfarColumns, long long* NwindowColumns, int* maxFar) {
-  if (!plan) return SPN_ERR_INVALID_ARGUMENT;
-  if (maxFar) *maxFar = plan->maxFar;
-  if (Nchunks) *Nchunks = plan->NC;
-  if (NfarColumns) *NfarColumns = plan->nfar;
-  if (NwindowColumns) *NwindowColumns = plan->winCols;
+                  sizeof(int) * (size_t)plan->Ncols;
   return SPN_SUCCESS;
 }
 
@@ -449,7 +334,6 @@ int spn_ogs_plan_scatter(spn_ogs_plan_t plan, int K, const void* gv, void* v, in
 int spn_debug_set(int key, int value) {
   if (key == 4 && value >= 0) { g_chunk_iters = value; return SPN_SUCCESS; }
   if (key == 5 && value >= 0) { g_chunk_iters_gather = value; return SPN_SUCCESS; }
-  if (key == 6) { g_use_win = value != 0; return SPN_SUCCESS; }
   return SPN_ERR_INVALID_ARGUMENT;
 }
 

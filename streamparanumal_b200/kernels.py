@@ -165,10 +165,6 @@ class OgsPlan:
         nt, nirr, nbytes = ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
         check(_lib.kernel_lib().spn_ogs_plan_info(self._h, ctypes.byref(nt), ctypes.byref(nirr), ctypes.byref(nbytes)))
         self.Ntiles, self.Nirregular, self.plan_bytes = nt.value, nirr.value, nbytes.value
-        nc, nfar, wcols, mf = ctypes.c_int(), ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int()
-        check(_lib.kernel_lib().spn_ogs_plan_window_info(self._h, ctypes.byref(nc), ctypes.byref(nfar), ctypes.byref(wcols),
-                                                         ctypes.byref(mf)))
-        self.Nchunks, self.Nfar, self.NwindowCols, self.maxFar = nc.value, nfar.value, wcols.value, mf.value
 
     def gather(self, K, v, gv, op=ADD):
         if gv.dtype != v.dtype:

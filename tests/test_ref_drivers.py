@@ -81,7 +81,7 @@ def test_every_reference_driver_runs_on_the_b200():
         assert r.returncode == 0, r.stderr
         m = re.fullmatch(rf"BS{n} = \[(\d+) ({NUM}) ({NUM}) +({NUM})\]; %{title} \[DOFs, elapsed, DOFs/s, BW \(GB/s\)\]\n", r.stdout)
         assert m, r.stdout
-        assert int(m.group(1)) == (48 << 20) // per_entry
+        assert int(m.group(1)) == (48 << 20) // per_entry[n]
     r = run([need(os.path.join(DRV, "BS0")), "-n", "100"])
     assert r.returncode == 0 and re.search(r"BS0 = \[100 ", r.stdout), r.stdout + r.stderr
     # the ogs drivers: the reference's mesh_t + ogs_t::Setup + ogsOperator_t on the device kernels; DOFs must equal what the

@@ -11,9 +11,6 @@ rs, ci = util.csr_from_ids(ids)
 Nt, Ng = ids.size, rs.size - 1
 d_rs, d_ci = torch.from_numpy(rs).cuda(), torch.from_numpy(ci).cuda()
 plan = K.OgsPlan(rs, d_rs, d_ci, Nt, colIds=None)
-if os.environ.get("OGS_WIN"):
-    from streamparanumal_b200 import _lib
-    _lib.kernel_lib().spn_debug_set(6, int(os.environ["OGS_WIN"]))
 v = torch.rand(Nt, dtype=torch.float64, device="cuda")
 gv = torch.empty(Ng, dtype=torch.float64, device="cuda")
 for _ in range(2):
