@@ -228,39 +228,58 @@ int spn_ogs_halo_combine_scatter(int Nrows, int NrowsP, int K, const int* cmbSta
  * (libs/ogs/ogsPairwise.cpp:115-152), the pack kernel stores every send slot STRAIGHT INTO THE
  * DESTINATION RANK'S RECEIVE BUFFER (P2P stores through NVSwitch) and, when the whole launch has
  * stored, raises a flag word in each destination (release at system scope).  The combine kernel of
- * the destination acquires the flags of its sources before it reads the receive buffer.  No
- * communication kernel, no SM taken from the interior operator, no host synchronisation.
- *   send side: slots [slot0[i], slot0[i+1]) go to destination i, slot slot0[i] landing at dst[i];
- *              flag[i] (in destination i's memory) is set to `epoch` once every slot is stored.
- *   wait side: flag[i] are LOCAL words written by source i; the kernel waits until each is >= epoch.
- * `counter` is a zero-initialised local device word used to detect the last block (self-resetting).
+ * the destination acquires the flags of its sources before it reads the receive buffer and, when the
+ * whole launch has read, raises an ACK word in each source.  No communication kernel, no SM taken
+ * from the interior operator, no host synchronisation.
+ *
+ * Every rank owns one block  [flag word per source rank | ack word per destination rank | receive
+ * half 0 | receive half 1].  Calls are numbered by an epoch kept in DEVICE memory (spn_p2p_state_t,
+ * advanced by the pack kernel itself), so a call carries no host-side value and a captured CUDA
+ * graph of it can be replayed.  Data of epoch e uses half e & 1.  Flow control: before a pack kernel
+ * stores into half h of destination d it waits until d has acknowledged this rank's previous send
+ * that used half h (state->lastSend[d][h]) — also when the neighbour relation of a mode is one-way
+ * (Trans / NoTrans of a Signed operator), where nothing else would throttle a pure sender.
+ *
+ * spn_p2p_plan_t (one per exchange mode) and spn_p2p_state_t (one per operator) live in device memory
+ * and are written by the host once at setup (spn_memcpy_h2d); state must start zeroed.
  * ---------------------------------------------------------------------- */
 #define SPN_P2P_MAX_PEERS 32
+#define SPN_P2P_MAX_RANKS 64
 #define SPN_IPC_HANDLE_BYTES 64
 typedef struct {
-  int npeers;
-  int slot0[SPN_P2P_MAX_PEERS + 1];
-  void* dst[SPN_P2P_MAX_PEERS];
-  unsigned long long* flag[SPN_P2P_MAX_PEERS];
-  unsigned long long epoch;
-  unsigned int* counter;
-} spn_p2p_send_t;
+  int nsend, nrecv;                                         /* destinations / sources of this mode */
+  int slot0[SPN_P2P_MAX_PEERS + 1];                         /* send slots [slot0[i], slot0[i+1]) go to destination i */
+  int dstRank[SPN_P2P_MAX_PEERS];                           /* its rank (index into state->lastSend) */
+  long long remoteOffset[SPN_P2P_MAX_PEERS];                /* slot at which my first entry lands in destination i's half */
+  void* dstHalf[2][SPN_P2P_MAX_PEERS];                      /* destination i's receive halves (peer memory) */
+  unsigned long long* flagRemote[SPN_P2P_MAX_PEERS];        /* in destination i's block: raised to the epoch after my stores */
+  const unsigned long long* ackLocal[SPN_P2P_MAX_PEERS];    /* in MY block: raised by destination i after it read */
+  const unsigned long long* flagLocal[SPN_P2P_MAX_PEERS];   /* in MY block: raised by source i */
+  unsigned long long* ackRemote[SPN_P2P_MAX_PEERS];         /* in source i's block: raised to the epoch after my reads */
+  const void* recvHalf[2];                                  /* my receive halves */
+} spn_p2p_plan_t;
 typedef struct {
-  int nsrc;
-  const unsigned long long* flag[SPN_P2P_MAX_PEERS];
-  unsigned long long epoch;
-} spn_p2p_wait_t;
+  unsigned long long epoch;                                 /* calls completed on this operator */
+  unsigned long long lastSend[SPN_P2P_MAX_RANKS][2];        /* per destination rank and half: epoch of my last send into it */
+  unsigned int packCounter, combineCounter;                 /* last-block detection, self-resetting */
+} spn_p2p_state_t;
 int spn_ipc_get_handle(void* dptr, void* handle64);            /* cudaIpcGetMemHandle of a spn_malloc block   */
 int spn_ipc_open_handle(const void* handle64, void** dptr);    /* map a peer's block (enables peer access)    */
 int spn_ipc_close_handle(void* dptr);
-/* spn_ogs_halo_gather_pack with the send slots stored into the destinations (sendBuf is not used) */
-int spn_ogs_halo_gather_pack_p2p(int Nrows, int Nsend, int K, const int* rowStarts, const int* colIds, const int* sendIds,
-                                 const void* v, void* ownBuf, const spn_p2p_send_t* send, int type, int op, spn_stream_t stream);
-/* spn_ogs_extract with the output stored into the destinations (Scatter NoTrans: owners send their rows) */
-int spn_ogs_extract_p2p(int N, int K, const int* ids, const void* q, const spn_p2p_send_t* send, int type, spn_stream_t stream);
-/* spn_ogs_halo_combine_scatter that first waits for the sources' flags */
+/* spn_ogs_halo_gather_pack with the send slots stored into the destinations: one fold per halo row, fanned out to the
+ * row's send slots rowSendDst[rowSendStarts[row] .. rowSendStarts[row+1]) (each: destination index << 24 | slot within
+ * that destination's message).  Always launched on a multi-rank operator, even with nothing to send: it advances the epoch. */
+int spn_ogs_halo_gather_pack_p2p(int Nrows, int K, const int* rowStarts, const int* colIds, const int* rowSendStarts,
+                                 const int* rowSendDst, const void* v, void* ownBuf, const spn_p2p_plan_t* d_plan,
+                                 spn_p2p_state_t* d_state, int type, int op, spn_stream_t stream);
+/* spn_ogs_extract with the output stored into the destinations (Scatter NoTrans: owners send their rows);
+ * slotDst[s] = destination index << 24 | slot within that destination's message */
+int spn_ogs_extract_p2p(int N, int K, const int* ids, const int* slotDst, const void* q, const spn_p2p_plan_t* d_plan,
+                        spn_p2p_state_t* d_state, int type, spn_stream_t stream);
+/* spn_ogs_halo_combine_scatter that first waits for the sources' flags, reads the receive half of the current epoch and
+ * acknowledges the sources (recvBuf is taken from the plan) */
 int spn_ogs_halo_combine_scatter_p2p(int Nrows, int NrowsP, int K, const int* cmbStarts, const int* cmbIds,
-                                     const void* ownBuf, const void* recvBuf, const spn_p2p_wait_t* wait,
+                                     const void* ownBuf, const spn_p2p_plan_t* d_plan, spn_p2p_state_t* d_state,
                                      const int* sRowStarts, const int* sColIds, void* out, int type, int op, spn_stream_t stream);
 
 /* ------------------------------------------------------------------------

@@ -79,12 +79,12 @@ KERNEL_SIGNATURES = {
     "spn_debug_set": [c_int, c_int],
     "spn_ogs_halo_gather_pack": [c_int, c_int, c_int, _IP, _IP, _IP, _P, _P, _P, c_int, c_int, _P],
     "spn_ogs_halo_combine_scatter": [c_int, c_int, c_int, _IP, _IP, _P, _P, _IP, _IP, _P, c_int, c_int, _P],
-    # peer-memory halo exchange (structs passed by pointer: spn_p2p_send_t / spn_p2p_wait_t)
+    # peer-memory halo exchange (spn_p2p_plan_t / spn_p2p_state_t live in device memory)
     "spn_ipc_get_handle": [_P, _P],
     "spn_ipc_open_handle": [_P, POINTER(c_void_p)],
     "spn_ipc_close_handle": [_P],
-    "spn_ogs_halo_gather_pack_p2p": [c_int, c_int, c_int, _IP, _IP, _IP, _P, _P, _P, c_int, c_int, _P],
-    "spn_ogs_extract_p2p": [c_int, c_int, _IP, _P, _P, c_int, _P],
+    "spn_ogs_halo_gather_pack_p2p": [c_int, c_int, _IP, _IP, _IP, _IP, _P, _P, _P, _P, c_int, c_int, _P],
+    "spn_ogs_extract_p2p": [c_int, c_int, _IP, _IP, _P, _P, _P, c_int, _P],
     "spn_ogs_halo_combine_scatter_p2p": [c_int, c_int, c_int, _IP, _IP, _P, _P, _P, _IP, _IP, _P, c_int, c_int, _P],
 }
 

@@ -93,6 +93,10 @@ struct ogsExchangeData_t {
   std::vector<dlong> sendCounts, sendOffsets, recvCounts, recvOffsets;  // per neighbour, in slots
   std::vector<dlong> cmbStarts, cmbIds;                  // Nrows+1 / Nrecv: receive slots of each row, ascending source rank
   deviceMemory<dlong> o_sendIds, o_cmbStarts, o_cmbIds;
+  // peer-memory exchange: send slots of every halo row (CSR over rows) and of every send slot, each entry
+  // (index of the destination in sendRanks) << 24 | slot within that destination's message
+  std::vector<dlong> rowSendStarts, rowSendDst, slotDst;
+  deviceMemory<dlong> o_rowSendStarts, o_rowSendDst, o_slotDst;
 };
 
 class ogs_t {
@@ -207,27 +211,29 @@ class ogs_t {
   bool exchange_in_flight = false;
 
   // peer-memory exchange (include/spn_b200.h "Peer-memory halo exchange"; csrc/ogs_halo.cu): every rank owns one
-  // IPC-shared block  [flags: one word per source rank | receive half 0 | receive half 1].  The pack kernel of a
-  // call stores its send slots into half (epoch & 1) of each destination and sets flags[me] = epoch there; the
-  // combine kernel waits for flags[src] >= epoch.  Two halves are enough: a rank cannot start call n+2 before its
-  // neighbours finished reading call n (its combine of n+1 waits for their pack of n+1, which follows their
-  // combine of n in stream order).  Used when an entry is <= 8 bytes (K*sizeof(T)); otherwise, or when IPC is not
-  // available or SPN_OGS_EXCHANGE=nccl, the NCCL send/recv path runs.
+  // IPC-shared block  [flag word per source rank | ack word per destination rank | receive half 0 | receive half 1].
+  // The pack kernel of a call stores its send slots into half (epoch & 1) of each destination and sets flag[me] = epoch
+  // there; the combine kernel waits for flag[src] >= epoch, reads, and sets ack[me] = epoch in each source.  A pack kernel
+  // does not store into half h of a destination before that destination acknowledged this rank's previous send into h —
+  // the flow control that also covers the one-way neighbour relations of the Trans / NoTrans modes.  The epoch and the
+  // per-destination send history live in device memory (spn_p2p_state_t), the address tables of each mode too
+  // (spn_p2p_plan_t), so a call passes no per-call value from the host.  Used when an entry (K*sizeof(T)) fits
+  // kPeerEntryBytes; otherwise, or when IPC is not available or SPN_OGS_EXCHANGE=nccl, the NCCL send/recv path runs.
+  static constexpr size_t kPeerEntryBytes = 32;  // receive slots are sized for K*sizeof(T) up to 4 doubles
   struct PeerExchange {
     bool enabled = false;
     deviceMemory<char> o_block;
-    deviceMemory<unsigned int> o_counter;
     size_t flagBytes = 0, halfBytes = 0;
-    std::vector<void*> peerBlock;        // [size]: mapped block of every neighbour, nullptr otherwise
-    std::vector<dlong> remoteOffset[3];  // [mode][i]: slot of my first entry in the receive buffer of sendRanks[i]
-    unsigned long long epoch = 0;
+    std::vector<void*> peerBlock;  // [size]: mapped block of every neighbour, nullptr otherwise
+    deviceMemory<char> o_plan;     // spn_p2p_plan_t[3], indexed by Transpose
+    deviceMemory<char> o_state;    // spn_p2p_state_t
   };
   PeerExchange p2p;
   void SetupPeerExchange();
   void FreePeerExchange();
-  bool UsePeerExchange(size_t Nbytes) const { return p2p.enabled && Nbytes <= sizeof(dfloat); }
-  void PeerSendTable(spn_p2p_send_t& s, int mode, size_t Nbytes);      // starts a new epoch
-  const void* PeerWaitTable(spn_p2p_wait_t& w, int mode) const;        // returns the receive half of the current epoch
+  bool UsePeerExchange(size_t Nbytes) const { return p2p.enabled && Nbytes <= kPeerEntryBytes; }
+  const spn_p2p_plan_t* PeerPlan(int mode) const { return reinterpret_cast<const spn_p2p_plan_t*>(p2p.o_plan.ptr()) + mode; }
+  spn_p2p_state_t* PeerState() const { return reinterpret_cast<spn_p2p_state_t*>(const_cast<char*>(p2p.o_state.ptr())); }
   bool peer_exchange_in_flight = false;
 
   // staging of the host-buffer operations

@@ -41,7 +41,9 @@ void ogsOperator_t::upload(platform_t& platform, bool tile_plans) {
   o_colIdsT = platform.malloc<dlong>(colIdsT);
   if (kind == Signed) {
     o_rowStartsN = platform.malloc<dlong>(rowStartsN);
-    if (nnzN) o_colIdsN = platform.malloc<dlong>(colIdsN);
+    // a rank that holds no positive copy of any row (nnzN == 0) still passes colIdsN to the kernels, whose every row
+    // is then empty: keep a one-entry array so that the handle is not null (the reference's kernels run on it as they are)
+    o_colIdsN = nnzN ? platform.malloc<dlong>(colIdsN) : platform.malloc<dlong>(std::vector<dlong>(1, 0));
   } else {
     o_rowStartsN = o_rowStartsT;
     o_colIdsN = o_colIdsT;
@@ -194,10 +196,8 @@ void ogs_t::GatherScatterStart(void* o_v, int k, Type type, Op op, Transpose tra
   const dlong* hCI = useN ? gatherHalo->o_colIdsN.ptr() : gatherHalo->o_colIdsT.ptr();
   if (comm.size() > 1 && UsePeerExchange((size_t)k * Sizeof(type))) {
     // partials go straight into the neighbours' receive buffers (P2P stores), flags raised by the same launch
-    spn_p2p_send_t send;
-    PeerSendTable(send, trans, (size_t)k * Sizeof(type));
-    SPN_CHECK(spn_ogs_halo_gather_pack_p2p(NhaloT, d.Nsend, k, hRS, hCI, d.o_sendIds.ptr(), o_v, o_ownBuf.ptr(), &send, type, op,
-                                           ForkHalo()));
+    SPN_CHECK(spn_ogs_halo_gather_pack_p2p(NhaloT, k, hRS, hCI, d.o_rowSendStarts.ptr(), d.o_rowSendDst.ptr(), o_v, o_ownBuf.ptr(),
+                                           PeerPlan(trans), PeerState(), type, op, ForkHalo()));
     peer_exchange_in_flight = true;
     return;
   }
@@ -219,10 +219,8 @@ void ogs_t::GatherScatterFinish(void* o_v, int k, Type type, Op op, Transpose tr
   const dlong* sRS = sN ? gatherHalo->o_rowStartsN.ptr() : gatherHalo->o_rowStartsT.ptr();
   const dlong* sCI = sN ? gatherHalo->o_colIdsN.ptr() : gatherHalo->o_colIdsT.ptr();
   if (peer_exchange_in_flight) {
-    spn_p2p_wait_t wait;
-    const void* recv = PeerWaitTable(wait, trans);
-    SPN_CHECK(spn_ogs_halo_combine_scatter_p2p(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), o_ownBuf.ptr(), recv,
-                                               &wait, sRS, sCI, o_v, type, op, hs));
+    SPN_CHECK(spn_ogs_halo_combine_scatter_p2p(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), o_ownBuf.ptr(),
+                                               PeerPlan(trans), PeerState(), sRS, sCI, o_v, type, op, hs));
     peer_exchange_in_flight = false;
     JoinHalo();
     return;
@@ -311,10 +309,9 @@ void ogs_t::GatherStart(void* o_gv, const void* o_v, int k, Type type, Op op, Tr
     AllocBuffer(Nbytes);
     const ogsExchangeData_t& d = data[Trans];
     if (comm.size() > 1 && UsePeerExchange(Nbytes)) {
-      spn_p2p_send_t send;
-      PeerSendTable(send, Trans, Nbytes);
-      SPN_CHECK(spn_ogs_halo_gather_pack_p2p(NhaloT, d.Nsend, k, gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(),
-                                             d.o_sendIds.ptr(), o_v, o_ownBuf.ptr(), &send, type, op, ForkHalo()));
+      SPN_CHECK(spn_ogs_halo_gather_pack_p2p(NhaloT, k, gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(),
+                                             d.o_rowSendStarts.ptr(), d.o_rowSendDst.ptr(), o_v, o_ownBuf.ptr(), PeerPlan(Trans),
+                                             PeerState(), type, op, ForkHalo()));
       peer_exchange_in_flight = true;
       return;
     }
@@ -337,11 +334,9 @@ void ogs_t::GatherFinish(void* o_gv, const void* o_v, int k, Type type, Op op, T
     const ogsExchangeData_t& d = data[Trans];
     const size_t Nbytes = (size_t)k * Sizeof(type);
     if (peer_exchange_in_flight) {
-      spn_p2p_wait_t wait;
-      const void* recv = PeerWaitTable(wait, Trans);
-      SPN_CHECK(spn_ogs_halo_combine_scatter_p2p(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), o_ownBuf.ptr(), recv,
-                                                 &wait, nullptr, nullptr, static_cast<char*>(o_gv) + Nbytes * (size_t)NlocalT,
-                                                 type, op, hs));
+      SPN_CHECK(spn_ogs_halo_combine_scatter_p2p(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), o_ownBuf.ptr(),
+                                                 PeerPlan(Trans), PeerState(), nullptr, nullptr,
+                                                 static_cast<char*>(o_gv) + Nbytes * (size_t)NlocalT, type, op, hs));
       peer_exchange_in_flight = false;
       JoinHalo();
       return;
@@ -367,10 +362,9 @@ void ogs_t::ScatterStart(void* /*o_v*/, const void* o_gv, int k, Type type, Tran
   const ogsExchangeData_t& d = data[NoTrans];
   // owners pack their rows of o_gv straight into send order (the reference copies, then extracts: ogs.cpp:423-431)
   if (comm.size() > 1 && UsePeerExchange(Nbytes)) {
-    spn_p2p_send_t send;
-    PeerSendTable(send, NoTrans, Nbytes);
-    SPN_CHECK(spn_ogs_extract_p2p(d.Nsend, k, d.o_sendIds.ptr(), static_cast<const char*>(o_gv) + Nbytes * (size_t)NlocalT, &send,
-                                  type, ForkHalo()));
+    SPN_CHECK(spn_ogs_extract_p2p(d.Nsend, k, d.o_sendIds.ptr(), d.o_slotDst.ptr(),
+                                  static_cast<const char*>(o_gv) + Nbytes * (size_t)NlocalT, PeerPlan(NoTrans), PeerState(), type,
+                                  ForkHalo()));
     peer_exchange_in_flight = true;
     return;
   }
@@ -391,10 +385,9 @@ void ogs_t::ScatterFinish(void* o_v, const void* o_gv, int k, Type type, Transpo
   if (trans == NoTrans) {
     const ogsExchangeData_t& d = data[NoTrans];
     if (peer_exchange_in_flight) {
-      spn_p2p_wait_t wait;
-      const void* recv = PeerWaitTable(wait, NoTrans);
-      SPN_CHECK(spn_ogs_halo_combine_scatter_p2p(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), gvHalo, recv, &wait,
-                                                 gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(), o_v, type, Add, hs));
+      SPN_CHECK(spn_ogs_halo_combine_scatter_p2p(d.Nrows, d.NrowsP, k, d.o_cmbStarts.ptr(), d.o_cmbIds.ptr(), gvHalo, PeerPlan(NoTrans),
+                                                 PeerState(), gatherHalo->o_rowStartsT.ptr(), gatherHalo->o_colIdsT.ptr(), o_v, type,
+                                                 Add, hs));
       peer_exchange_in_flight = false;
       JoinHalo();
       return;

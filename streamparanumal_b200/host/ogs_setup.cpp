@@ -13,6 +13,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <numeric>
 #include <omp.h>
 #include <parallel/algorithm>
@@ -224,16 +225,18 @@ void ogs_t::SetupPeerExchange() {
   comm.Allreduce(want, Comm::Min);
   if (!want) return;
 
+  SPN_ABORT("peer exchange: more ranks than SPN_P2P_MAX_RANKS", size > SPN_P2P_MAX_RANKS);
   dlong maxRecv = 0;
   for (int m = 0; m < 3; ++m) maxRecv = std::max(maxRecv, data[m].Nrecv);
   auto align = [](size_t b) { return (b + 255) / 256 * 256; };
-  p2p.flagBytes = align(sizeof(unsigned long long) * (size_t)size);
-  p2p.halfBytes = align(sizeof(dfloat) * (size_t)std::max<dlong>(maxRecv, 1));
+  p2p.flagBytes = align(2 * sizeof(unsigned long long) * (size_t)size);  // flags, then acks
+  p2p.halfBytes = align(kPeerEntryBytes * (size_t)std::max<dlong>(maxRecv, 1));
   const size_t blockBytes = p2p.flagBytes + 2 * p2p.halfBytes;
   p2p.o_block = platform.malloc<char>(blockBytes);
-  p2p.o_counter = platform.malloc<unsigned int>(1);
+  p2p.o_state = platform.malloc<char>(sizeof(spn_p2p_state_t));
+  p2p.o_plan = platform.malloc<char>(3 * sizeof(spn_p2p_plan_t));
   SPN_CHECK(spn_memset(p2p.o_block.ptr(), 0, blockBytes, platform.getStream()));
-  SPN_CHECK(spn_memset(p2p.o_counter.ptr(), 0, sizeof(unsigned int), platform.getStream()));
+  SPN_CHECK(spn_memset(p2p.o_state.ptr(), 0, sizeof(spn_p2p_state_t), platform.getStream()));
   platform.finish();
 
   // handles of every rank's block
@@ -259,17 +262,44 @@ void ogs_t::SetupPeerExchange() {
   }
   comm.Allreduce(ok, Comm::Min);
 
-  // where my entries land in each destination: the destination's recvOffsets entry for me, per mode
+  // address tables of the three modes: where my entries land in each destination (its recvOffsets entry for me),
+  // which words to raise and which to watch
+  std::vector<spn_p2p_plan_t> plans(3);
+  memset(plans.data(), 0, sizeof(spn_p2p_plan_t) * 3);
+  char* myBlock = p2p.o_block.ptr();
+  const size_t ackBase = sizeof(unsigned long long) * (size_t)size;
   for (int m = 0; m < 3; ++m) {
+    const ogsExchangeData_t& d = data[m];
     std::vector<dlong> tell((size_t)size, -1), got((size_t)size, -1);
-    for (size_t i = 0; i < data[m].recvRanks.size(); ++i) tell[data[m].recvRanks[i]] = data[m].recvOffsets[i];
+    for (size_t i = 0; i < d.recvRanks.size(); ++i) tell[d.recvRanks[i]] = d.recvOffsets[i];
     comm.Alltoall(tell.data(), got.data());
-    p2p.remoteOffset[m].assign(data[m].sendRanks.size(), 0);
-    for (size_t i = 0; i < data[m].sendRanks.size(); ++i) {
-      const dlong off = got[data[m].sendRanks[i]];
-      if (off < 0) ok = 0;  // the destination does not expect me: plans disagree
-      p2p.remoteOffset[m][i] = off;
+    if (!ok) continue;  // (the collective above still has to run on every rank)
+    spn_p2p_plan_t& pl = plans[m];
+    pl.nsend = (int)d.sendRanks.size();
+    pl.nrecv = (int)d.recvRanks.size();
+    for (int i = 0; i < pl.nsend; ++i) {
+      const int r = d.sendRanks[i];
+      char* block = static_cast<char*>(p2p.peerBlock[r]);
+      const dlong off = got[r];
+      if (off < 0 || !block) { ok = 0; break; }  // the destination does not expect me: plans disagree
+      pl.slot0[i] = d.sendOffsets[i];
+      pl.dstRank[i] = r;
+      pl.remoteOffset[i] = off;
+      pl.dstHalf[0][i] = block + p2p.flagBytes;
+      pl.dstHalf[1][i] = block + p2p.flagBytes + p2p.halfBytes;
+      pl.flagRemote[i] = reinterpret_cast<unsigned long long*>(block) + rank;
+      pl.ackLocal[i] = reinterpret_cast<const unsigned long long*>(myBlock + ackBase) + r;
     }
+    pl.slot0[pl.nsend] = d.Nsend;
+    for (int i = 0; i < pl.nrecv && ok; ++i) {
+      const int r = d.recvRanks[i];
+      char* block = static_cast<char*>(p2p.peerBlock[r]);
+      if (!block) { ok = 0; break; }
+      pl.flagLocal[i] = reinterpret_cast<const unsigned long long*>(myBlock) + r;
+      pl.ackRemote[i] = reinterpret_cast<unsigned long long*>(block + ackBase) + rank;
+    }
+    pl.recvHalf[0] = myBlock + p2p.flagBytes;
+    pl.recvHalf[1] = myBlock + p2p.flagBytes + p2p.halfBytes;
   }
   comm.Allreduce(ok, Comm::Min);
   if (!ok) {
@@ -277,32 +307,8 @@ void ogs_t::SetupPeerExchange() {
     FreePeerExchange();
     return;
   }
+  SPN_CHECK(spn_memcpy_h2d(p2p.o_plan.ptr(), plans.data(), sizeof(spn_p2p_plan_t) * 3, platform.getStream(), 0));
   p2p.enabled = true;
-}
-
-void ogs_t::PeerSendTable(spn_p2p_send_t& s, int mode, size_t Nbytes) {
-  const ogsExchangeData_t& d = data[mode];
-  const unsigned long long epoch = ++p2p.epoch;
-  const size_t half = p2p.flagBytes + (size_t)(epoch & 1ull) * p2p.halfBytes;
-  s.npeers = (int)d.sendRanks.size();
-  for (int i = 0; i < s.npeers; ++i) {
-    char* block = static_cast<char*>(p2p.peerBlock[d.sendRanks[i]]);
-    s.slot0[i] = d.sendOffsets[i];
-    s.dst[i] = block + half + (size_t)p2p.remoteOffset[mode][i] * Nbytes;
-    s.flag[i] = reinterpret_cast<unsigned long long*>(block) + comm.rank();
-  }
-  s.slot0[s.npeers] = d.Nsend;
-  s.epoch = epoch;
-  s.counter = p2p.o_counter.ptr();
-}
-
-const void* ogs_t::PeerWaitTable(spn_p2p_wait_t& w, int mode) const {
-  const ogsExchangeData_t& d = data[mode];
-  w.nsrc = (int)d.recvRanks.size();
-  for (int i = 0; i < w.nsrc; ++i)
-    w.flag[i] = reinterpret_cast<const unsigned long long*>(p2p.o_block.ptr()) + d.recvRanks[i];
-  w.epoch = p2p.epoch;
-  return p2p.o_block.ptr() + p2p.flagBytes + (size_t)(p2p.epoch & 1ull) * p2p.halfBytes;
 }
 
 void ogs_t::AssertGatherDefined() const {
@@ -331,11 +337,19 @@ void ogs_t::Setup(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_, co
       d.o_sendIds = data[Sym].o_sendIds;
       d.o_cmbStarts = data[Sym].o_cmbStarts;
       d.o_cmbIds = data[Sym].o_cmbIds;
+      d.o_rowSendStarts = data[Sym].o_rowSendStarts;
+      d.o_rowSendDst = data[Sym].o_rowSendDst;
+      d.o_slotDst = data[Sym].o_slotDst;
       continue;
     }
     if (d.Nsend) d.o_sendIds = platform.malloc<dlong>(d.sendIds);
     if (d.Nrows) d.o_cmbStarts = platform.malloc<dlong>(d.cmbStarts);
     if (d.Nrecv) d.o_cmbIds = platform.malloc<dlong>(d.cmbIds);
+    if (NhaloT) d.o_rowSendStarts = platform.malloc<dlong>(d.rowSendStarts);
+    if (d.Nsend) {
+      d.o_rowSendDst = platform.malloc<dlong>(d.rowSendDst);
+      d.o_slotDst = platform.malloc<dlong>(d.slotDst);
+    }
   }
   if (comm.size() > 1) {
     commStream = platform.createStream();
@@ -626,6 +640,17 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
     d.cmbIds.resize((size_t)d.Nrecv);
     std::vector<dlong> fill(d.cmbStarts.begin(), d.cmbStarts.end() - 1);
     for (dlong i = 0; i < d.Nrecv; ++i) d.cmbIds[fill[d.recvRows[i]]++] = i;
+    // send slots of every halo row, for the peer-memory pack kernel (one fold per row, fanned out)
+    SPN_ABORT("ogs setup: more send slots per neighbour than the peer exchange encodes", d.Nsend >= (1 << 24));
+    d.slotDst.resize((size_t)d.Nsend);
+    for (size_t p = 0; p < d.sendRanks.size(); ++p)
+      for (dlong q = 0; q < d.sendCounts[p]; ++q) d.slotDst[d.sendOffsets[p] + q] = (dlong)((p << 24) | (size_t)q);
+    d.rowSendStarts.assign((size_t)NhaloT + 1, 0);
+    for (dlong i = 0; i < d.Nsend; ++i) d.rowSendStarts[d.sendIds[i] + 1]++;
+    for (dlong r = 0; r < NhaloT; ++r) d.rowSendStarts[r + 1] += d.rowSendStarts[r];
+    d.rowSendDst.resize((size_t)d.Nsend);
+    std::vector<dlong> fill2(d.rowSendStarts.begin(), d.rowSendStarts.end() - 1);
+    for (dlong i = 0; i < d.Nsend; ++i) d.rowSendDst[fill2[d.sendIds[i]]++] = d.slotDst[i];
   }
 }
 

@@ -291,3 +291,95 @@ def test_multirank_halo_t(world, K, dtype, exchange):
         pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")
     with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
         mp.spawn(_halo_worker, args=(world, _free_port(), tmpdir, K, dtype, exchange), nprocs=world, join=True)
+
+
+# ------------------------------------------------------------------------- one-way neighbours, back-to-back calls
+def _oneway_worker(rank, world, port, tmpdir, exchange):
+    """All positive copies on rank 0, so in the Trans plan rank 1 only SENDS and rank 0 only RECEIVES (and the reverse in
+    NoTrans): nothing but the ack words of the peer-memory exchange throttles the pure sender.  25 Gather(Trans) calls
+    back to back with no host synchronisation (what BS6 does), with the receiver's stream held up by a long kernel
+    first, then the same for Scatter(NoTrans) (BS7); every call's result is checked afterwards.  Rank 1 holds no
+    positive copy of any halo row (its N operator is empty)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["LOCAL_RANK"] = str(rank)
+    os.environ["SPN_OGS_EXCHANGE"] = exchange
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ogs_sim
+        from streamparanumal_b200 import host
+        torch.cuda.set_device(rank)
+        dev = f"cuda:{rank}"
+        comm = host.Comm(rank, world, rendezvous=tmpdir)
+        platform = host.Platform(comm, rank)
+        ids, _ = host.box_hex_ids(rank, world, 3, 3, 3, 5)
+        ids = np.abs(ids)
+        # the caller picks the positive copies (unique = false): the first copy on rank 0, none anywhere else
+        gathered = [None] * world
+        dist.all_gather_object(gathered, ids)
+        on0 = set(np.unique(gathered[0]).tolist())
+        signed = ids.copy()
+        seen = set()
+        for i, lab in enumerate(ids.tolist()):
+            positive = (rank == 0 and lab not in seen) or (rank != 0 and lab not in on0 and lab not in seen)
+            seen.add(lab)
+            if not positive:
+                signed[i] = -lab
+        ogs = host.Ogs(signed, comm, kind=host.SIGNED, unique=False, platform=platform)
+        assert ogs.gather_defined and ogs.NhaloT > 0
+        if rank != 0:
+            assert ogs.NhaloP == 0 and ogs.halo_nnzN == 0      # no positive copy of any shared row here
+        t = ogs.exchange_info(host.TRANS)
+        assert (t["Nsend"] == 0) == (rank == 0) and (t["Nrecv"] == 0) == (rank != 0)   # one-way
+        plan = ogs_sim.Plan(ogs)
+        ncalls = 25
+        vs = [_values(ids.size, np.float64, 1000 + 10 * c + rank) for c in range(ncalls)]
+        d_vs = [torch.from_numpy(v).to(dev) for v in vs]
+        d_gs = [torch.zeros(max(ogs.Ngather, 1), dtype=torch.float64, device=dev) for _ in range(ncalls)]
+        big = torch.ones(1 << 27, dtype=torch.float64, device=dev)
+        dist.barrier()
+        if rank == 0:
+            for _ in range(20):
+                big.mul_(1.0000001)   # ~ 10 ms of queued work in front of the receiver's first combine
+        for c in range(ncalls):
+            ogs.Gather(d_gs[c], d_vs[c], 1, host.ADD, host.TRANS)     # no host synchronisation in the loop
+        torch.cuda.synchronize()
+        for c in range(ncalls):
+            exp = ogs_sim.gather(plan, vs[c], K=1, op=host.ADD, trans=host.TRANS)
+            assert np.array_equal(d_gs[c].cpu().numpy()[: ogs.Ngather], exp[: ogs.Ngather]), f"Gather(Trans) call {c}"
+        # Scatter(NoTrans): rank 0 only sends, rank 1 only receives; this time the sender runs ahead of a delayed receiver
+        gqs = [_values(max(ogs.Ngather, 1), np.float64, 2000 + 10 * c + rank) for c in range(ncalls)]
+        d_gqs = [torch.from_numpy(g).to(dev) for g in gqs]
+        d_outs = [torch.zeros(ids.size, dtype=torch.float64, device=dev) for _ in range(ncalls)]
+        dist.barrier()
+        if rank == 1:
+            for _ in range(20):
+                big.mul_(1.0000001)
+        for c in range(ncalls):
+            ogs.Scatter(d_outs[c], d_gqs[c], 1, host.NOTRANS)
+        torch.cuda.synchronize()
+        for c in range(ncalls):
+            exp = ogs_sim.scatter(plan, gqs[c][: ogs.Ngather], np.zeros(ids.size), K=1, trans=host.NOTRANS)
+            assert np.array_equal(d_outs[c].cpu().numpy(), exp), f"Scatter(NoTrans) call {c}"
+        # GatherScatter in the one-way modes on the rank without positives (null-free N operator)
+        _check_all_modes(ogs, plan, rank, 1, np.float64, dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ogs.close()
+        platform.close()
+        comm.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_multirank_one_way_neighbours_back_to_back(exchange):
+    import torch.multiprocessing as mp
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")
+    with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
+        mp.spawn(_oneway_worker, args=(world, _free_port(), tmpdir, exchange), nprocs=world, join=True)
