@@ -91,6 +91,14 @@ int spn_event_record(spn_event_t ev, spn_stream_t stream);
 int spn_event_sync(spn_event_t ev);
 int spn_stream_wait_event(spn_stream_t stream, spn_event_t ev);
 int spn_event_elapsed_ms(spn_event_t start, spn_event_t stop, float* ms);
+/* CUDA graphs: a sequence of launches and event fork/joins enqueued between begin and end on `stream` (and on the streams
+ * that wait on its events) is recorded instead of run, and replayed with one call — the launch-bound small-size tail
+ * (BASELINE.json configs[4]; the reference pays 2-3 device.finish() per ogs call: libs/ogs/ogs.cpp:74,104,117). */
+typedef void* spn_graph_t;  /* cudaGraphExec_t */
+int spn_graph_begin_capture(spn_stream_t stream);
+int spn_graph_end_capture(spn_stream_t stream, spn_graph_t* graph);
+int spn_graph_launch(spn_graph_t graph, spn_stream_t stream);
+int spn_graph_destroy(spn_graph_t graph);
 
 /* ------------------------------------------------------------------------
  * BS0–BS5 streaming kernels (FP64 = dfloat, include/types.h:33-69).

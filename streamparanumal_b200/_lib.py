@@ -52,6 +52,10 @@ KERNEL_SIGNATURES = {
     "spn_event_sync": [_P],
     "spn_stream_wait_event": [_P, _P],
     "spn_event_elapsed_ms": [_P, _P, POINTER(c_float)],
+    "spn_graph_begin_capture": [_P],
+    "spn_graph_end_capture": [_P, POINTER(c_void_p)],
+    "spn_graph_launch": [_P, _P],
+    "spn_graph_destroy": [_P],
     "spn_bs0": [c_int, _P, _P, _P],
     "spn_copy_f64": [c_int64, _P, _P, _P],
     "spn_axpby_f64": [c_int64, c_double, _P, c_double, _P, _P],

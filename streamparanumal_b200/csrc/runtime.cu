@@ -171,6 +171,32 @@ int spn_event_elapsed_ms(spn_event_t start, spn_event_t stop, float* ms) {
   return SPN_SUCCESS;
 }
 
+int spn_graph_begin_capture(spn_stream_t stream) {
+  SPN_CUDA_TRY(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeThreadLocal));
+  return SPN_SUCCESS;
+}
+int spn_graph_end_capture(spn_stream_t stream, spn_graph_t* graph) {
+  if (!graph) return SPN_ERR_INVALID_ARGUMENT;
+  *graph = nullptr;
+  cudaGraph_t g = nullptr;
+  SPN_CUDA_TRY(cudaStreamEndCapture(as_stream(stream), &g));
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return (int)e; }
+  *graph = reinterpret_cast<spn_graph_t>(exec);
+  return SPN_SUCCESS;
+}
+int spn_graph_launch(spn_graph_t graph, spn_stream_t stream) {
+  if (!graph) return SPN_ERR_INVALID_ARGUMENT;
+  SPN_CUDA_TRY(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph), as_stream(stream)));
+  return SPN_SUCCESS;
+}
+int spn_graph_destroy(spn_graph_t graph) {
+  if (graph) SPN_CUDA_TRY(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph)));
+  return SPN_SUCCESS;
+}
+
 int spn_stream_create_priority(spn_stream_t* stream, int high) {
   if (!stream) return SPN_ERR_INVALID_ARGUMENT;
   int lo = 0, hi = 0;

@@ -170,8 +170,7 @@ int spn_host_ogs_halo_labels(spn_host_ogs_t h, const long long** ptr, long long*
 int spn_host_ogs_gather_scatter(spn_host_ogs_t h, void* v, int k, int type, int op, int trans) {
   if (!h) return SPN_ERR_INVALID_ARGUMENT;
   return guarded([&] {
-    h->ogs.GatherScatterStart(v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans);
-    h->ogs.GatherScatterFinish(v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans);
+    h->ogs.GatherScatter(v, k, (ogs::Type)type, (ogs::Op)op, (ogs::Transpose)trans);
   });
 }
 int spn_host_ogs_gather_scatter_start(spn_host_ogs_t h, void* v, int k, int type, int op, int trans) {

@@ -132,6 +132,11 @@ class ogs_t {
   void Free();
 
   // ---- device operations: raw-pointer core (type-erased), used by the templates and the C API ----
+  // Start + Finish.  On a multi-rank operator with the peer-memory exchange the whole call (fork, halo pack, interior
+  // operator, halo combine, join: 3 launches + 4 event operations) is captured ONCE per (vector, k, type, op, trans,
+  // stream) into a CUDA graph and replayed afterwards — possible because a call passes no per-call value from the host
+  // (the epoch lives in device memory).  SPN_OGS_GRAPH=0 disables it.
+  void GatherScatter(void* o_v, int k, Type type, Op op, Transpose trans);
   void GatherScatterStart(void* o_v, int k, Type type, Op op, Transpose trans);
   void GatherScatterFinish(void* o_v, int k, Type type, Op op, Transpose trans);
   void GatherStart(void* o_gv, const void* o_v, int k, Type type, Op op, Transpose trans);
@@ -159,8 +164,7 @@ class ogs_t {
 
   // ---- the reference's signatures (include/ogs.hpp:251-341) ----
   template <typename T> void GatherScatter(deviceMemory<T> o_v, const int k, const Op op, const Transpose trans) {
-    GatherScatterStart(o_v, k, op, trans);
-    GatherScatterFinish(o_v, k, op, trans);
+    GatherScatter(o_v.ptr(), k, ogsType<T>::get(), op, trans);
   }
   template <typename T> void GatherScatterStart(deviceMemory<T> o_v, const int k, const Op op, const Transpose trans) {
     GatherScatterStart(o_v.ptr(), k, ogsType<T>::get(), op, trans);
@@ -235,6 +239,18 @@ class ogs_t {
   const spn_p2p_plan_t* PeerPlan(int mode) const { return reinterpret_cast<const spn_p2p_plan_t*>(p2p.o_plan.ptr()) + mode; }
   spn_p2p_state_t* PeerState() const { return reinterpret_cast<spn_p2p_state_t*>(const_cast<char*>(p2p.o_state.ptr())); }
   bool peer_exchange_in_flight = false;
+
+  // captured calls (see GatherScatter): second call with the same key captures, later calls replay
+  struct CallGraph {
+    void* o_v = nullptr;
+    spn_stream_t stream = nullptr;
+    int k = 0, type = 0, op = 0, trans = 0, seen = 0;
+    spn_graph_t graph = nullptr;
+  };
+  std::vector<CallGraph> graphs;
+  spn_stream_t graphStream = nullptr;  // recording stream (owned by the platform)
+  int use_graphs = -1;  // -1: not decided yet
+  void FreeGraphs();
 
   // staging of the host-buffer operations
   struct HostStage {

@@ -175,6 +175,7 @@ void ogs_t::Free() {
   if (forkEvent) { spn_event_destroy(forkEvent); forkEvent = nullptr; }
   if (joinEvent) { spn_event_destroy(joinEvent); joinEvent = nullptr; }
   halo_forked = false;
+  FreeGraphs();
   FreePeerExchange();
   for (HostStage& st : stage) {
     if (st.busy) spn_event_sync(st.d2hDone);
