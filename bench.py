@@ -15,9 +15,16 @@ With --suite (default on at 1 GPU) the same JSON line carries a `suite` object w
 effective GB/s of every BS1-BS8 kernel at its BASELINE.json size and BS0 us/launch,
 bytes counted the way the reference counts them.
 
---impl reference times the reference's own CPU kernels (oracle/_ref: the OKL sources
-compiled for the host; plus the OpenMP-threaded restatement of the reference's host
-twins) on a bounded sample of the same workload on this box's host cores.
+At N > 1 the line also carries `strong` (the same call with 64^3 elements IN TOTAL, BASELINE.json configs[3]) and, at every
+N, `tail` (BS0 launch latency, BS5 at 1 KB - 1 MB, BS8 at 2^3 - 8^3 elements per rank: configs[4]).  Before anything is timed
+every rank runs checked calls (`parity_checked`): all-ones -> the node multiplicity computed from the lattice position alone,
+a label-valued vector -> multiplicity x value (both exact, both need the halo exchange to be right), and at one rank the
+full-size result against the CPU oracle on the plan's CSR.
+
+--impl reference times the reference's OWN CPU path on this box's host cores: oracle/_ref/libref_ogs.so is the reference's
+libs/core + primitives + ogs compiled unchanged (oracle/Makefile), so the call timed is its mesh.ogs.GatherScatter(q, 1, Add, Sym)
+on the SAME 64^3 degree-7 mesh — the OpenMP-threaded host-memory overload and the `-m Serial` device path, the faster one
+reported.  Without that library (no /root/reference at build time) the OpenMP restatement in oracle/ stands in (kind "port").
 """
 import argparse
 import json
@@ -45,9 +52,14 @@ def bs8_bytes(Nt, Ng):
     return 4 * (Ng + 1) + 4 * Nt + 8 * Nt + 8 * Nt
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one BS8 launch at the headline size, from the ncu --set full
-# capture summarised in profiles/ (None until a capture at this size is committed)
-TRAFFIC_BS8 = 2639159000  # profiles/r01_ncu_full_summary_f3_ogs.txt: 1.611656 GB read + 1.027503 GB written (64^3, degree 7)
+def measured_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the round's ncu --set full capture
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when no capture is committed"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
 
 
 def bs6_bytes(Nt, Ng):
@@ -119,61 +131,70 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # reference arm (CPU)
 # --------------------------------------------------------------------------------------
+def reference_cpu(nx, p, steps, warmup, budget_s=None):
+    """Times the reference's CPU path for BS8 on an nx^3 degree-p box.  Returns (results, Nt, Ng): results maps a variant
+    name to {"t": seconds per call, "kind": "reference" | "port", "cores": threads}.  budget_s: keep calling for about
+    that many seconds instead of a fixed step count."""
+    import spn_paths  # noqa: F401
+    from streamparanumal_b200 import host, synth
+    from oracle import pyoracle, refogs
+    cores = os.cpu_count() or 1
+    ids, nglobal = host.box_hex_ids(0, 1, nx, nx, nx, p)
+    Nt = ids.size
+    results = {}
+    if refogs.available():
+        r = refogs.RefOgs(ids, kind=refogs.SIGNED, unique=True)   # libp::ogs::ogs_t::Setup, as mesh_t::GatherScatterSetup calls it
+        Ng = r.NgatherGlobal
+        assert Ng == nglobal
+        for name, path in (("reference host-memory overload (OpenMP host operator)", 0), ("reference -m Serial (OKL kernel)", 1)):
+            if budget_s is not None:
+                t1, th = r.time_gather_scatter(path, 1, 1)
+                n = max(1, min(200, int(budget_s / max(t1, 1e-9))))
+                t, th = r.time_gather_scatter(path, n, 0)
+            else:
+                t, th = r.time_gather_scatter(path, steps, warmup)
+            results[name] = {"t": t, "kind": "reference", "cores": th if path == 0 else 1}
+        r.close()
+    else:
+        o = host.Ogs(ids.copy(), host.Comm(0, 1, None), kind=host.SIGNED, unique=True, platform=None)
+        rs, ci = o.array("local_rowStartsT"), o.array("local_colIdsT")
+        Ng = o.NgatherGlobal
+        q = synth.splitmix64(Nt, 3)
+        fn = lambda: pyoracle.ogs_gather_scatter(rs, ci, rs, ci, q, threads=cores)
+        for _ in range(max(1, warmup if budget_s is None else 1)):
+            fn()
+        t0 = time.perf_counter()
+        n = 0
+        while (n < steps) if budget_s is None else (time.perf_counter() - t0 < budget_s):
+            fn()
+            n += 1
+        results["OpenMP restatement of the host operator (oracle/)"] = {"t": (time.perf_counter() - t0) / n, "kind": "port", "cores": cores}
+    return results, Nt, Ng
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import spn_testutil as util
-    from oracle import pyoracle
-
-    cores = os.cpu_count() or 1
-    nx = args.ref_nx
-    ids = util.hex_ids(nx, nx, nx, args.p)
-    rs, ci = util.csr_from_ids(ids)
-    Nt, Ng = ids.size, rs.size - 1
-    q = util.splitmix64(Nt, 3)
-    have_ref = pyoracle.have_ref()
-    blocks = pyoracle.block_rows(rs, 512) if have_ref else None
-
-    def ref_serial():
-        # the reference's gatherScatter OKL kernel, Serial semantics.  OCCA's OpenMP mode puts its
-        # parallel-for on the k<K loop (one iteration here), so this is also the OpenMP-mode speed.
-        pyoracle.ref_ogs_gather_scatter(blocks, rs, ci, rs, ci, q)
-
-    def port_threaded():
-        # restatement of the reference's threaded host twin (libs/ogs/ogsOperator.cpp:340-409)
-        pyoracle.ogs_gather_scatter(rs, ci, rs, ci, q, threads=cores)
-
-    def time_fn(fn):
-        for _ in range(args.warmup):
-            fn()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            fn()
-        return (time.perf_counter() - t0) / args.steps
-
-    results = {}
-    if have_ref:
-        results["reference"] = time_fn(ref_serial)
-    results["port"] = time_fn(port_threaded)
-    kind = min(results, key=results.get)
-    t = results[kind]
+    nx = args.ref_nx if args.ref_nx else args.nx
+    results, Nt, Ng = reference_cpu(nx, args.p, args.steps, args.warmup)
+    best = min(results, key=lambda k: results[k]["t"])
+    t, kind, cores = results[best]["t"], results[best]["kind"], results[best]["cores"]
     value = Ng / t * 1e-9
-    sample = (f"BS8 gatherScatter on a {nx}^3 degree-{args.p} hex box (Nt={Nt}, Ng={Ng}), "
-              f"{args.steps} calls after {args.warmup} warm-ups; host arrays (pyoracle copies v per call)")
+    sample = (f"{best}: mesh.ogs.GatherScatter(q, 1, Add, Sym) on the {nx}^3 degree-{args.p} hex box (Nt={Nt}, Ng={Ng}), "
+              f"{args.steps} calls after {args.warmup} warm-ups, q resident in the reference's own containers")
     line = {
         "impl": "reference", "metric": "BS8 gather+scatter throughput (DOFs/s, NgatherGlobal per call time)",
         "value": value, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BS8 ogs gatherScatter, hex p={args.p}, {nx}^3 elements (bounded CPU sample of the 64^3 workload)",
+        "config": {"workload": f"BS8 ogs_t::GatherScatter(Add,Sym,K=1), hex p={args.p}, {nx}^3 elements "
+                               f"(mpirun -np 1 ./BS8 -m Serial -nx {nx} -ny {nx} -nz {nx} -p {args.p})",
                    "nx": nx, "p": args.p, "Nt": Nt, "Ng": Ng},
         "effective_gbs": bs8_bytes(Nt, Ng) / t * 1e-9,
-        "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": cores if kind == "port" else 1, "kind": kind,
-                         "sample": sample,
-                         "all": {k: {"GDOF/s": Ng / v * 1e-9, "GB/s": bs8_bytes(Nt, Ng) / v * 1e-9,
-                                     "cores": cores if k == "port" else 1} for k, v in results.items()}},
+        "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": cores, "kind": kind, "sample": sample,
+                         "all": {k: {"GDOF/s": Ng / v["t"] * 1e-9, "GB/s": bs8_bytes(Nt, Ng) / v["t"] * 1e-9, "cores": v["cores"],
+                                     "kind": v["kind"]} for k, v in results.items()}},
         "e2e": {"value": value, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -245,14 +266,100 @@ def run_suite(torch, K, peak, ogs_ctx):
     return out
 
 
+def parity_checks(torch, host, ogs, labels, rank, world, nx, p, full_oracle):
+    """Independent expectations for ogs_t::GatherScatter(Add, Sym) on this rank's brick, exact in FP64:
+      ones        -> the multiplicity of every node in the GLOBAL mesh, computed from the lattice position alone;
+      g(label)    -> multiplicity x g(label)   (g integer-valued: a slot paired with the wrong label shows up);
+      at one rank -> the CPU oracle walking the plan's CSR on seeded uniform(-1,1) data, bit for bit (full size)."""
+    from streamparanumal_b200 import synth
+    grid, rxyz = host.rank_grid(rank, world)
+    mult = synth.box_multiplicity(rxyz, grid, (nx, nx, nx), p).astype(np.float64)
+    n = labels.size
+    out = {"checks": []}
+    q = torch.ones(n, dtype=torch.float64, device="cuda")
+    for rep in range(3):   # three calls: both receive halves of the peer exchange and the replayed graph are exercised
+        q.fill_(1.0)
+        ogs.GatherScatter(q, 1, host.ADD, host.SYM)
+    ok1 = bool(np.array_equal(q.cpu().numpy(), mult))
+    out["checks"].append({"all-ones -> lattice multiplicity": ok1})
+    g = ((labels % 1021) - 510).astype(np.float64)
+    q.copy_(torch.from_numpy(g))
+    ogs.GatherScatter(q, 1, host.ADD, host.SYM)
+    ok2 = bool(np.array_equal(q.cpu().numpy(), mult * g))
+    out["checks"].append({"g(label) -> multiplicity * g(label)": ok2})
+    ok3 = True
+    if full_oracle:
+        from oracle import pyoracle   # the checker, not the thing measured
+        rs, ci = ogs.array("local_rowStartsT"), ogs.array("local_colIdsT")
+        x = synth.splitmix64(n, 77)
+        q.copy_(torch.from_numpy(x))
+        ogs.GatherScatter(q, 1, host.ADD, host.SYM)
+        exp = pyoracle.ogs_gather_scatter(rs, ci, rs, ci, x, threads=os.cpu_count() or 1)
+        ok3 = bool(np.array_equal(q.cpu().numpy().view(np.int64), exp.view(np.int64)))
+        out["checks"].append({"full-size result == CPU oracle on the plan's CSR (bit for bit)": ok3})
+    out["ok"] = ok1 and ok2 and ok3
+    del q
+    return out
+
+
+def strong_scaling(torch, dist, host, comm, platform, rank, world, p, timed):
+    """BASELINE.json configs[3], strong: 64^3 elements IN TOTAL split over the process grid (-nx 32 at 8 ranks)"""
+    from streamparanumal_b200 import synth
+    grid, _ = host.rank_grid(rank, world)
+    n = tuple(64 // g for g in grid)
+    ids, _ = host.box_hex_ids(rank, world, n[0], n[1], n[2], p)
+    ogs = host.Ogs(ids, comm, kind=host.SIGNED, unique=True, platform=platform)
+    q = torch.from_numpy(synth.splitmix64(ids.size, 5 + rank)).cuda()
+    t = timed(lambda: ogs.GatherScatter(q, 1, host.ADD, host.SYM), 50, 5)
+    Ng, Nt = ogs.NgatherGlobal, ids.size * world
+    res = {"elements_per_rank": list(n), "Ng": Ng, "ms_per_step": t * 1e3, "GDOF/s": Ng / t * 1e-9,
+           "effective_gbs": bs8_bytes(Nt, Ng) / t * 1e-9, "note": "64^3 degree-7 elements in total; speed-up over 1 GPU = this GDOF/s / the 1-GPU value"}
+    ogs.close()
+    return res
+
+
+def latency_tail(torch, dist, host, K, comm, platform, rank, world, p, timed):
+    """BASELINE.json configs[4]: BS0 launch latency, BS5 at 1 KB - 1 MB (with the scalar allreduce at N > 1), BS8 at 2^3 - 8^3
+    elements per rank — the launch-bound end of the sweeps (BS/BS8/runBS8.sh:76-90, BS/BS5/runBS5.sh)"""
+    from streamparanumal_b200 import synth
+    out = {"BS8_us": {}, "BS5_us": {}}
+    for nx in (2, 4, 8):
+        ids, _ = host.box_hex_ids(rank, world, nx, nx, nx, p)
+        ogs = host.Ogs(ids, comm, kind=host.SIGNED, unique=True, platform=platform)
+        q = torch.from_numpy(synth.splitmix64(ids.size, 9 + rank)).cuda()
+        t = timed(lambda: ogs.GatherScatter(q, 1, host.ADD, host.SYM), 200, 20)
+        out["BS8_us"][f"nx={nx}"] = round(t * 1e6, 2)
+        ogs.close()
+    o = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for nbytes in (1024, 16384, 262144, 1048576):
+        n = nbytes // 24
+        Ap = torch.rand(n, dtype=torch.float64, device="cuda")
+        r = torch.zeros(n, dtype=torch.float64, device="cuda")
+
+        def call():
+            K.cg_update(n, Ap, 1.0, r, o)
+            if world > 1:
+                comm.allreduce_device(o)
+        out["BS5_us"][f"{nbytes} B"] = round(timed(call, 200, 20) * 1e6, 2)
+    a = torch.zeros(8, dtype=torch.float64, device="cuda")
+    for _ in range(100):
+        K.bs0(1, a, a)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(1000):
+        K.bs0(1, a, a)
+    torch.cuda.synchronize()
+    out["BS0_us_per_launch"] = round((time.perf_counter() - t0) / 1000 * 1e6, 2)
+    return out
+
+
 def run_b200(args):
     import ctypes
     import torch
     import torch.distributed as dist
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import spn_testutil as util
     from streamparanumal_b200 import kernels as K
     from streamparanumal_b200 import _lib, host
+    from streamparanumal_b200 import synth as util
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -281,7 +388,12 @@ def run_b200(args):
     Nt, Ng = Nt_local * world, ogs.NgatherGlobal  # bs8Run.cpp:52-56: Nelements*Np summed over ranks, ogs.NgatherGlobal
     assert Ng == nglobal, "ogs setup lost labels"
     halo = ogs.exchange_info(host.SYM)
+    labels = np.abs(ogs.ids)
     del ids
+
+    # ---- checked calls before anything is timed (every rank; the exchange the timed loop uses) ----
+    parity = parity_checks(torch, host, ogs, labels, rank, world, nx, p, full_oracle=(world == 1))
+    del labels
     q = torch.from_numpy(util.splitmix64(Nt_local, 3 + rank)).cuda()
 
     step = lambda: ogs.GatherScatter(q, 1, host.ADD, host.SYM)  # mesh.ogs.GatherScatter(o_q, 1, ogs::Add, ogs::Sym)
@@ -398,13 +510,25 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": bytes_rank,
                      "basis": "per GPU: reference-counted bytes of one call / ranks / step time"
                               + ("" if world == 1 else " (step = halo pack [+ exchange] + interior kernel + halo combine)"),
-                     "traffic": TRAFFIC_BS8 if (world == 1 and nx == 64 and p == 7) else None},
+                     "traffic": measured_traffic("bs8_gather_scatter_64_p7") if (world == 1 and nx == 64 and p == 7) else None},
         "e2e": {"value": Ng / t_e2e * 1e-9, "unit": "GDOF/s", "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
                 "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
                 "api": "ogs_t::GatherScatterStart/Finish(pinned host q): H2D -> GatherScatter -> D2H per step, two vectors in flight"},
         "gpu_launches": args.steps * launches_per_step,
         "clocks": clocks,
+        "parity_checked": parity["ok"], "parity": parity,
     }
+    if world > 1:
+        ok = torch.tensor([1 if parity["ok"] else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        line["parity_checked"] = bool(ok.item())
+    if not line["parity_checked"]:
+        raise SystemExit(f"bench.py: parity check failed on rank {rank}: {parity}")
+
+    if args.strong and world > 1:
+        line["strong"] = strong_scaling(torch, dist, host, comm, platform, rank, world, p, timed)
+    if args.tail:
+        line["tail"] = latency_tail(torch, dist, host, K, comm, platform, rank, world, p, timed)
 
     if args.suite and world == 1:
         line["suite"] = run_suite(torch, K, peak, (ogs, Nt, Ng, q))
@@ -429,38 +553,16 @@ def run_b200(args):
 
 
 def cpu_baseline(args):
-    """The reference's CPU kernels on this box's host cores, bounded sample (rank 0, N=1)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import spn_testutil as util
-    from oracle import pyoracle
-    cores = os.cpu_count() or 1
-    nx = args.ref_nx
-    ids = util.hex_ids(nx, nx, nx, args.p)
-    rs, ci = util.csr_from_ids(ids)
-    Nt, Ng = ids.size, rs.size - 1
-    q = util.splitmix64(Nt, 3)
-    res = {}
-    if pyoracle.have_ref():
-        blocks = pyoracle.block_rows(rs, 512)
-        pyoracle.ref_ogs_gather_scatter(blocks, rs, ci, rs, ci, q)
-        t0 = time.perf_counter()
-        n = 0
-        while time.perf_counter() - t0 < 6.0:
-            pyoracle.ref_ogs_gather_scatter(blocks, rs, ci, rs, ci, q)
-            n += 1
-        res["reference"] = (time.perf_counter() - t0) / n
-    pyoracle.ogs_gather_scatter(rs, ci, rs, ci, q, threads=cores)
-    t0 = time.perf_counter()
-    n = 0
-    while time.perf_counter() - t0 < 6.0:
-        pyoracle.ogs_gather_scatter(rs, ci, rs, ci, q, threads=cores)
-        n += 1
-    res["port"] = (time.perf_counter() - t0) / n
-    kind = min(res, key=res.get)
-    return {"value": Ng / res[kind] * 1e-9, "unit": "GDOF/s", "cores": cores if kind == "port" else 1, "kind": kind,
-            "sample": f"BS8 gatherScatter, {nx}^3 degree-{args.p} hex box (Nt={Nt}), ~6 s per variant",
-            "all": {k: {"GDOF/s": Ng / v * 1e-9, "GB/s": bs8_bytes(Nt, Ng) / v * 1e-9, "cores": cores if k == "port" else 1}
-                    for k, v in res.items()}}
+    """The reference's CPU path on this box's host cores, bounded sample (rank 0, N=1): about 10 s per variant on a
+    32^3 box of the same degree (the full 64^3 run is what `--impl reference` times)."""
+    nx = args.cpu_nx
+    results, Nt, Ng = reference_cpu(nx, args.p, 0, 0, budget_s=8.0)
+    best = min(results, key=lambda k: results[k]["t"])
+    v = results[best]
+    return {"value": Ng / v["t"] * 1e-9, "unit": "GDOF/s", "cores": v["cores"], "kind": v["kind"],
+            "sample": f"{best}: BS8 gatherScatter, {nx}^3 degree-{args.p} hex box (Nt={Nt}, Ng={Ng}), ~8 s of calls per variant",
+            "all": {k: {"GDOF/s": Ng / r["t"] * 1e-9, "GB/s": bs8_bytes(Nt, Ng) / r["t"] * 1e-9, "cores": r["cores"], "kind": r["kind"]}
+                    for k, r in results.items()}}
 
 
 def main():
@@ -471,7 +573,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=64, help="elements per direction per rank (reference -nx/-ny/-nz)")
     ap.add_argument("--p", type=int, default=7, help="polynomial degree (reference -p)")
-    ap.add_argument("--ref-nx", type=int, default=24, help="CPU sample size for the reference arm / cpu_baseline")
+    ap.add_argument("--ref-nx", type=int, default=0, help="--impl reference: elements per direction (0 = --nx, the same workload)")
+    ap.add_argument("--cpu-nx", type=int, default=32, help="cpu_baseline: elements per direction of the bounded CPU sample")
+    ap.add_argument("--no-tail", dest="tail", action="store_false")
+    ap.add_argument("--no-strong", dest="strong", action="store_false")
     ap.add_argument("--no-suite", dest="suite", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

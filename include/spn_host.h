@@ -44,6 +44,8 @@ int spn_host_platform_finish(spn_host_platform_t platform);                     
 /* ---- mesh labels: mesh_t::SetupBoxHex3D + ConnectNodes for the box (libs/mesh/meshSetupBoxHex3D.cpp) ---- */
 /* ids[nx*ny*nz*(p+1)^3]; *Nglobal = number of distinct labels over all ranks */
 int spn_host_box_hex_ids(int rank, int size, int nx, int ny, int nz, int p, long long* ids, long long* Nglobal);
+/* process grid of the box (libs/core/rankDecomp.cpp:55-91,166-213): out[6] = size_x, size_y, size_z, rank_x, rank_y, rank_z */
+int spn_host_rank_grid(int rank, int size, int* out);
 
 /* ---- ogs_t (include/ogs.hpp:216-341) --------------------------------------------------------------- */
 typedef struct spn_host_ogs* spn_host_ogs_t;

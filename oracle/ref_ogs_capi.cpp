@@ -5,6 +5,8 @@
 // "device" (compiled OKL kernels) Gather / Scatter / GatherScatter on the CPU, and (iii) the global node ids of the
 // reference's box-hex mesh (libs/mesh/meshSetupBoxHex3D.cpp, meshConnectNodes.cpp:44-81).
 // One rank (the MPI stand-in of include/shim/mpi.h).  Nothing under streamparanumal_b200/ links this.
+#include <omp.h>
+
 #include <cstring>
 #include <string>
 
@@ -12,6 +14,7 @@
 #include "ogs.hpp"
 #include "ogs/ogsOperator.hpp"
 #include "platform.hpp"
+#include "timer.hpp"
 
 using namespace libp;
 
@@ -162,6 +165,39 @@ int ref_ogs_gather_scatter_device(void* handle, void* v, int k, int type, int op
     memcpy(v, m.ptr(), n * sizeof(T));
   });
   return 0;
+}
+
+// Times `steps` calls of the reference's own BS8 operation, mesh.ogs.GatherScatter(q, 1, ogs::Add, ogs::Sym)
+// (BS/BS8/src/bs8Run.cpp:47-57), after `warmup` calls, on FP64 data resident in the reference's own containers:
+//   path 0: the host-memory overload (memory<dfloat>; libs/ogs/ogs.cpp:127-204 -> the OpenMP-threaded host operator,
+//           libs/ogs/ogsOperator.cpp:340-409)
+//   path 1: the device-memory overload on the Serial backend (deviceMemory<dfloat> -> kernel_t -> the OKL gatherScatter
+//           kernel), i.e. what `BS8 -m Serial` times
+// Returns seconds per call; *threads = OpenMP threads the reference configured (platformDeviceConfig.cpp:103-150).
+double ref_ogs_time_gather_scatter(void* handle, int path, int steps, int warmup, int* threads) {
+  Handle* h = static_cast<Handle*>(handle);
+  const size_t n = (size_t)h->ogs.N;
+  memory<dfloat> q(n);
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) q[i] = (dfloat)((i * 2654435761ull) % 2001) * 1e-3 - 1.0;
+  if (threads) {
+#pragma omp parallel
+    {
+#pragma omp single
+      *threads = omp_get_num_threads();
+    }
+  }
+  deviceMemory<dfloat> o_q;
+  if (path == 1) o_q = env().platform.malloc<dfloat>(q);
+  auto call = [&]() {
+    if (path == 1) h->ogs.GatherScatter(o_q, 1, ogs::Add, ogs::Sym);
+    else h->ogs.GatherScatter(q, 1, ogs::Add, ogs::Sym);
+  };
+  for (int i = 0; i < warmup; ++i) call();
+  const timePoint_t t0 = Time();
+  for (int i = 0; i < steps; ++i) call();
+  const timePoint_t t1 = Time();
+  return ElapsedTime(t0, t1) / (steps > 0 ? steps : 1);
 }
 
 // global node ids of the reference's own box mesh of degree-p hex elements (one rank): ids_out has nx*ny*nz*(p+1)^3

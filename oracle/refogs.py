@@ -36,6 +36,8 @@ def lib():
         l.ref_ogs_gather_scatter_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int]
         l.ref_ogs_gather.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]
         l.ref_ogs_scatter.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]
+        l.ref_ogs_time_gather_scatter.restype = ctypes.c_double
+        l.ref_ogs_time_gather_scatter.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_int)]
         l.ref_mesh_box_hex_ids.restype = c_longlong
         l.ref_mesh_box_hex_ids.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_longlong]
         _lib = l
@@ -94,6 +96,13 @@ class RefOgs:
         rc = lib().ref_ogs_scatter(self._h, v.ctypes.data, gvp.ctypes.data, k, _TYPES[v.dtype], trans)
         assert rc == 0
         return v
+
+    def time_gather_scatter(self, path, steps, warmup):
+        """seconds per call of the reference's mesh.ogs.GatherScatter(q, 1, Add, Sym): path 0 = host-memory overload
+        (OpenMP host operator), path 1 = deviceMemory on the Serial backend (its OKL kernel); returns (seconds, threads)"""
+        th = c_int()
+        t = lib().ref_ogs_time_gather_scatter(self._h, int(path), int(steps), int(warmup), byref(th))
+        return float(t), th.value
 
     def close(self):
         if self._h:

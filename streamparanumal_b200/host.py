@@ -34,6 +34,7 @@ _HOST_SIGNATURES = {
     "spn_host_platform_set_stream": [c_void_p, c_void_p],
     "spn_host_platform_finish": [c_void_p],
     "spn_host_box_hex_ids": [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, POINTER(c_longlong)],
+    "spn_host_rank_grid": [c_int, c_int, c_void_p],
     "spn_host_ogs_setup": [POINTER(c_void_p), c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "spn_host_ogs_free": [c_void_p],
     "spn_host_ogs_info": [c_void_p, c_void_p],
@@ -148,6 +149,13 @@ def box_hex_ids(rank, size, nx, ny, nz, p):
     ng = c_longlong()
     _check(host_lib().spn_host_box_hex_ids(rank, size, nx, ny, nz, p, ids.ctypes.data, byref(ng)), "box_hex_ids")
     return ids, ng.value
+
+
+def rank_grid(rank, size):
+    """((size_x, size_y, size_z), (rank_x, rank_y, rank_z)) of the box's process grid"""
+    out = (c_int * 6)()
+    _check(host_lib().spn_host_rank_grid(int(rank), int(size), out), "rank_grid")
+    return tuple(out[:3]), tuple(out[3:])
 
 
 _ARRAYS = {"local_rowStartsT": 0, "local_colIdsT": 1, "local_rowStartsN": 2, "local_colIdsN": 3,

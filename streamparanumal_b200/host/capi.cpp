@@ -81,6 +81,13 @@ int spn_host_platform_finish(spn_host_platform_t platform) {
   return guarded([&] { platform->platform.finish(); });
 }
 
+int spn_host_rank_grid(int rank, int size, int* out) {
+  if (!out || size < 1 || rank < 0 || rank >= size) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] {
+    Factor3(size, out[0], out[1], out[2]);
+    RankDecomp3(out[0], out[1], out[2], out[3], out[4], out[5], rank);
+  });
+}
 int spn_host_box_hex_ids(int rank, int size, int nx, int ny, int nz, int p, long long* ids, long long* Nglobal) {
   if (!ids || size < 1 || rank < 0 || rank >= size || nx < 1 || ny < 1 || nz < 1 || p < 1) return SPN_ERR_INVALID_ARGUMENT;
   return guarded([&] { BoxHexGlobalIds(rank, size, nx, ny, nz, p, ids, Nglobal); });

@@ -11,13 +11,7 @@ def exact_b(n):
     return ((np.arange(n, dtype=np.int64) % 5) - 2).astype(np.float64)
 
 
-def splitmix64(n, seed):
-    """counter-based generator -> uniform(-1,1) doubles with 53-bit mantissas"""
-    z = (np.arange(n, dtype=np.uint64) + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
-    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-    z = z ^ (z >> np.uint64(31))
-    return (z >> np.uint64(11)).astype(np.float64) * (2.0 / (1 << 53)) - 1.0
+from streamparanumal_b200.synth import splitmix64  # noqa: F401  (one generator for the tests and the benchmark)
 
 
 def hex_ids(nx, ny, nz, p):
