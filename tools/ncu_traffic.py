@@ -25,10 +25,9 @@ def main():
             i = hdr.index(k)
             return float(r[i].replace(",", "")) * UNIT[units[i]]
         total = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
-        if "ogs_tile_pf_kernel" in name and ", 2, " in name.split("<")[1]:
-            res["bs8_gather_scatter_64_p7"] = int(total)
-        elif "ogs_tile_pf_kernel" in name:
-            res["bs6_gather_64_p7"] = int(total)
+        if "ogs_tile_pf_kernel" in name:  # template arguments: T, OP, MODE (0 gather, 2 gather+scatter), ...
+            mode = name.split("<")[1].split(",")[2].strip()
+            res["bs8_gather_scatter_64_p7" if mode == "2" else "bs6_gather_64_p7"] = int(total)
     with open(os.path.join(ROOT, "profiles", "r02_traffic.json"), "w") as f:
         json.dump(res, f, indent=1)
     print(res)
