@@ -1,6 +1,7 @@
 // C-ABI entry points for the ogs kernels (include/spn_b200.h).  `type`/`op`
 // select a precompiled instantiation where the reference JIT-compiles one OKL
 // kernel per (T, OGS_OP) pair (libs/ogs/ogsUtils.cpp:46-123).
+#include <atomic>
 #include "ogs_pipe.cuh"
 
 #ifndef SPN_OGS_THREADS
@@ -19,7 +20,7 @@ void launch_pipe(dim3 grid, cudaStream_t st, int K, const int* bs, const int* rs
                  const T* in, T* out) {
   auto kern = ogs_pipe_kernel<T, OP, MODE, SPN_OGS_THREADS>;
   constexpr size_t smem = ogs_pipe_smem_bytes<T, MODE>();
-  static int resident[64];  // CTAs per device, 0 = not yet queried
+  static std::atomic<int> resident[64];  // CTAs per device ordinal, 0 = not yet queried (every thread would store the same value)
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
@@ -32,7 +33,8 @@ void launch_pipe(dim3 grid, cudaStream_t st, int K, const int* bs, const int* rs
     resident[dev] = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
   }
   const int NB = (int)grid.x;
-  const dim3 pgrid(NB < resident[dev] ? NB : resident[dev], grid.y);
+  const int cap = resident[dev].load();
+  const dim3 pgrid(NB < cap ? NB : cap, grid.y);
   kern<<<pgrid, SPN_OGS_THREADS, smem, st>>>(NB, K, bs, rs, ci, in, out);
 }
 

@@ -3,6 +3,7 @@
 // rowStarts/colIds/blockRowStarts; here the row partition is a warp-tile plan, see
 // ogs_tile.cuh) and its three kernels (libs/ogs/ogsOperator.cpp:176-204,295-322,442-481).
 #include <algorithm>
+#include <atomic>
 #include <new>
 #include <vector>
 #include "ogs_tile.cuh"
@@ -77,13 +78,22 @@ namespace {
 int g_chunk_iters = 8;
 int g_chunk_iters_gather = 0;
 
+// resident CTAs per SM of a kernel, cached PER DEVICE (the cache of one instantiation is an array indexed by the device
+// ordinal; entries are written once with the value every thread would compute, through relaxed atomics)
+struct OccupancyCache {
+  std::atomic<int> per_device[64];
+};
 template <typename K>
-int resident_ctas(K kern, int threads, int* cache) {
-  if (!*cache) {
+int resident_ctas(K kern, int threads, int device, OccupancyCache& cache, int* out) {
+  std::atomic<int>& slot = cache.per_device[device & 63];
+  int v = slot.load(std::memory_order_relaxed);
+  if (!v) {
     int per_sm = 0;
     SPN_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
-    *cache = per_sm > 0 ? per_sm : 1;
+    v = per_sm > 0 ? per_sm : 1;
+    slot.store(v, std::memory_order_relaxed);
   }
+  *out = v;
   return SPN_SUCCESS;
 }
 
@@ -102,8 +112,9 @@ int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaSt
       constexpr int M2 = (MODE == TILE_SCATTER) ? TILE_GATHER : MODE;  // (scatter never reaches this kernel)
       constexpr int PTH = TileGeom<MODE>::PF_TH, PMB = TileGeom<MODE>::PF_MINB;
       auto kern = ogs_tile_pf_kernel<T, OP, M2, U, PTH, PMB>;
-      static int res = 0;
-      rc = resident_ctas(kern, PTH, &res);
+      static OccupancyCache cache;
+      int res = 0;
+      rc = resident_ctas(kern, PTH, d->device, cache, &res);
       if (rc) return rc;
       const int pf_ctas_needed = (warps_needed + PTH / 32 - 1) / (PTH / 32);
       const int iters = (MODE == TILE_GATHER) ? g_chunk_iters_gather : g_chunk_iters;
@@ -114,14 +125,16 @@ int launch_tiles(const spn_ogs_plan* p, int K, const void* in, void* out, cudaSt
         kern<<<std::min(pf_ctas_needed, res * d->sms), PTH, 0, st>>>(NT, 0, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
     } else if (K == 1) {
       auto kern = ogs_tile_kernel<T, OP, MODE, U, true, TH, MB>;
-      static int res = 0;
-      rc = resident_ctas(kern, TH, &res);
+      static OccupancyCache cache;
+      int res = 0;
+      rc = resident_ctas(kern, TH, d->device, cache, &res);
       if (rc) return rc;
       kern<<<std::min(ctas_needed, res * d->sms), TH, 0, st>>>(NT, K, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
     } else {
       auto kern = ogs_tile_kernel<T, OP, MODE, U, false, TH, MB>;
-      static int res = 0;
-      rc = resident_ctas(kern, TH, &res);
+      static OccupancyCache cache;
+      int res = 0;
+      rc = resident_ctas(kern, TH, d->device, cache, &res);
       if (rc) return rc;
       kern<<<std::min(ctas_needed, res * d->sms), TH, 0, st>>>(NT, K, colP, p->d_row0, static_cast<const T*>(in), static_cast<T*>(out));
     }

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <thread>
 
 namespace spn {
@@ -93,6 +94,18 @@ sockaddr_un make_addr(const std::string& path) {
 
 }  // namespace
 
+namespace {
+// 64-bit token of the job a rank belongs to: ranks of different jobs that meet in one rendezvous directory refuse each other
+uint64_t job_token(const std::string& dir) {
+  std::string key = dir;
+  for (const char* name : {"TORCHELASTIC_RUN_ID", "MASTER_ADDR", "MASTER_PORT", "SPN_JOB_ID"})
+    if (const char* v = getenv(name)) { key += '|'; key += v; }
+  uint64_t h = 1469598103934665603ull;  // FNV-1a
+  for (unsigned char c : key) { h ^= c; h *= 1099511628211ull; }
+  return h;
+}
+}  // namespace
+
 comm_t::comm_t(int rank, int size, const std::string& dir) : rank_(rank), size_(size) {
   SPN_ABORT("invalid rank/size", size < 1 || rank < 0 || rank >= size);
   impl_ = std::make_shared<Impl>();
@@ -118,8 +131,8 @@ comm_t::comm_t(int rank, int size, const std::string& dir) : rank_(rank), size_(
       const int fd = socket(AF_UNIX, SOCK_STREAM, 0);
       SPN_ABORT("socket() failed", fd < 0);
       if (connect(fd, (const sockaddr*)&peer, sizeof(peer)) == 0) {
-        const int32_t hello = rank;
-        write_all_blocking(fd, &hello, sizeof(hello));
+        const uint64_t hello[2] = {(uint64_t)rank, job_token(dir)};
+        write_all_blocking(fd, hello, sizeof(hello));
         impl_->fd[r] = fd;
         break;
       }
@@ -136,8 +149,11 @@ comm_t::comm_t(int rank, int size, const std::string& dir) : rank_(rank), size_(
     SPN_ABORT("rendezvous timed out in accept", poll(&pf, 1, kTimeoutMs) <= 0);
     const int fd = accept(impl_->listen_fd, nullptr, nullptr);
     SPN_ABORT("accept failed", fd < 0);
-    int32_t hello = -1;
-    read_all_blocking(fd, &hello, sizeof(hello));
+    uint64_t hello2[2] = {~0ull, 0};
+    read_all_blocking(fd, hello2, sizeof(hello2));
+    SPN_ABORT("rendezvous: a rank of another job connected to " + impl_->sock_path + " (set SPN_RENDEZVOUS to a private directory)",
+              hello2[1] != job_token(dir));
+    const int hello = (int)hello2[0];
     SPN_ABORT("bad rendezvous hello", hello <= rank || hello >= size || impl_->fd[hello] >= 0);
     impl_->fd[hello] = fd;
   }
@@ -157,8 +173,11 @@ comm_t comm_t::World() {
   std::string dir;
   if (const char* d = getenv("SPN_RENDEZVOUS")) dir = d;
   else {
+    // one directory per job: the launcher's run id / port when there is one, else the parent process (ranks forked by one shell)
     const char* port = getenv("MASTER_PORT");
-    dir = std::string("/tmp/spn_rdv_") + std::to_string((long)getuid()) + "_" + (port ? port : "0");
+    const char* run = getenv("TORCHELASTIC_RUN_ID");
+    dir = std::string("/tmp/spn_rdv_") + std::to_string((long)getuid()) + "_" + (port ? port : "0") + "_" +
+          (run ? std::to_string(std::hash<std::string>{}(run) % 1000003) : std::string("p") + std::to_string((long)getppid()));
   }
   return comm_t(rank, size, dir);
 }

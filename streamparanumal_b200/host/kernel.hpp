@@ -9,7 +9,6 @@
 // A call enqueues on the platform's current stream and returns (occa::kernel::operator() on the
 // CUDA backend: occa/src/occa/internal/modes/cuda/kernel.cpp:74-101).
 #pragma once
-#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -53,6 +52,7 @@ struct kernelArg_t {
   long long i = 0;
   double d = 0.0;
   void* p = nullptr;
+  kernelArg_t() : kind(Int) {}
   kernelArg_t(int v) : kind(Int), i(v) {}
   kernelArg_t(long long v) : kind(Int), i(v) {}
   kernelArg_t(double v) : kind(Double), d(v) {}
@@ -63,26 +63,31 @@ struct kernelArg_t {
 
 class kernel_t {
  public:
-  using impl_t = std::function<int(const std::vector<kernelArg_t>&, spn_stream_t)>;
+  // plain function pointer + a small context word (ogs kernels: element type | reduction op << 8): a call costs no heap
+  // allocation and no std::function indirection (BS0 measures exactly this path)
+  using impl_t = int (*)(const kernelArg_t* args, spn_stream_t stream, int ctx);
+  static constexpr int kMaxArgs = 8;
   kernel_t() = default;
-  kernel_t(std::string name, size_t nargs, impl_t impl, std::shared_ptr<spn_stream_t> cur)
-      : name_(std::move(name)), nargs_(nargs), impl_(std::move(impl)), cur_(std::move(cur)) {}
-  bool isInitialized() const { return (bool)impl_; }
+  kernel_t(std::string name, int nargs, impl_t impl, int ctx, std::shared_ptr<spn_stream_t> cur)
+      : name_(std::move(name)), nargs_(nargs), impl_(impl), ctx_(ctx), cur_(std::move(cur)) {}
+  bool isInitialized() const { return impl_ != nullptr; }
   const std::string& name() const { return name_; }
 
   template <typename... Args>
   void operator()(Args&&... args) const {
+    static_assert(sizeof...(Args) <= (size_t)kMaxArgs, "no kernel of this path takes more than 8 arguments");
     SPN_ABORT("kernel_t: call of an uninitialised kernel", !impl_);
-    const std::vector<kernelArg_t> a{kernelArg_t(std::forward<Args>(args))...};
-    SPN_ABORT("kernel " + name_ + ": expected " + std::to_string(nargs_) + " arguments, got " + std::to_string(a.size()),
-              a.size() != nargs_);
-    check_status(impl_(a, cur_ ? *cur_ : nullptr), name_.c_str());
+    const kernelArg_t a[kMaxArgs] = {kernelArg_t(std::forward<Args>(args))...};
+    SPN_ABORT("kernel " + name_ + ": expected " + std::to_string(nargs_) + " arguments, got " + std::to_string(sizeof...(Args)),
+              (int)sizeof...(Args) != nargs_);
+    check_status(impl_(a, cur_ ? *cur_ : nullptr, ctx_), name_.c_str());
   }
 
  private:
   std::string name_;
-  size_t nargs_ = 0;
-  impl_t impl_;
+  int nargs_ = 0;
+  impl_t impl_ = nullptr;
+  int ctx_ = 0;
   std::shared_ptr<spn_stream_t> cur_;
 };
 

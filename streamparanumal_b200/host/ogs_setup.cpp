@@ -170,8 +170,7 @@ void SetPositivePickOrder(int mode) { g_pick_mode = mode ? 1 : 0; }
 void ogs_t::Free() {
   if (packedEvent) { spn_event_destroy(packedEvent); packedEvent = nullptr; }
   if (recvEvent) { spn_event_destroy(recvEvent); recvEvent = nullptr; }
-  commStream = nullptr;  // owned by the platform
-  haloStream = nullptr;
+
   if (forkEvent) { spn_event_destroy(forkEvent); forkEvent = nullptr; }
   if (joinEvent) { spn_event_destroy(joinEvent); joinEvent = nullptr; }
   halo_forked = false;
@@ -185,7 +184,11 @@ void ogs_t::Free() {
     st = HostStage();
   }
   nextStage = 0;
-  h2dStream = d2hStream = nullptr;  // owned by the platform
+  // every Setup makes its own streams: give them back (a platform outlives many ogs_t)
+  for (spn_stream_t* st : {&commStream, &haloStream, &graphStream, &h2dStream, &d2hStream}) {
+    platform.destroyStream(*st);
+    *st = nullptr;
+  }
   gatherLocal = nullptr;
   gatherHalo = nullptr;
   for (auto& d : data) d = ogsExchangeData_t();

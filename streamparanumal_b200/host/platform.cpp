@@ -1,3 +1,5 @@
+#include <algorithm>
+
 #include "platform.hpp"
 
 #include <cstdlib>
@@ -29,6 +31,15 @@ spn_stream_t platform_t::createStream(bool high_priority) {
   else SPN_CHECK(spn_stream_create(&s));
   state_->owned.push_back(s);
   return s;
+}
+
+void platform_t::destroyStream(spn_stream_t s) {
+  if (!s || !state_) return;
+  auto it = std::find(state_->owned.begin(), state_->owned.end(), s);
+  if (it == state_->owned.end()) return;
+  spn_stream_sync(s);
+  spn_stream_destroy(s);
+  state_->owned.erase(it);
 }
 
 timePoint_t Time() { return std::chrono::high_resolution_clock::now(); }

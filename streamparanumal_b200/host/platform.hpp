@@ -158,6 +158,7 @@ class platform_t {
   spn_stream_t getStream() const { return *state_->current; }
   void setStream(spn_stream_t s) { *state_->current = s; }
   spn_stream_t createStream(bool high_priority = false);
+  void destroyStream(spn_stream_t s);  // a stream made by createStream (waits for its work); null is a no-op
   void finish() { SPN_CHECK(spn_stream_sync(*state_->current)); }  // device.finish()
   const std::shared_ptr<spn_stream_t>& streamSlot() const { return state_->current; }
 
