@@ -480,6 +480,35 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t_, op=dist.ReduceOp.MAX)
     t_e2e = float(t_.item())
+
+    # copy-only ceiling of the same step: the two pinned vectors moved H2D and D2H concurrently on two streams, no kernel.
+    # (On this pool the boxes expose ONE NUMA node — nvidia-smi topo: every GPU "CPU Affinity 0-31, NUMA 0" — so there is
+    # nothing to bind ranks to; what the e2e number can reach at N ranks is what the host side sustains for N such copies.)
+    d_a = torch.empty(Nt_local, dtype=torch.float64, device="cuda")
+    d_b = torch.empty(Nt_local, dtype=torch.float64, device="cuda")
+    s_up, s_dn = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(lib.spn_stream_create(ctypes.byref(s_up)), "stream")
+    _lib.check(lib.spn_stream_create(ctypes.byref(s_dn)), "stream")
+
+    def copy_pair():
+        _lib.check(lib.spn_memcpy_h2d(d_a.data_ptr(), hbuf[0], nbytes, s_up, 1), "h2d")
+        _lib.check(lib.spn_memcpy_d2h(hbuf[1], d_b.data_ptr(), nbytes, s_dn, 1), "d2h")
+
+    for _ in range(2):
+        copy_pair()
+    lib.spn_stream_sync(s_up); lib.spn_stream_sync(s_dn)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        copy_pair()
+    lib.spn_stream_sync(s_up); lib.spn_stream_sync(s_dn)
+    t_copy = torch.tensor([(time.perf_counter() - t0) / 4], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_copy, op=dist.ReduceOp.MAX)
+    t_copy = float(t_copy.item())
+    lib.spn_stream_destroy(s_up); lib.spn_stream_destroy(s_dn)
+    del d_a, d_b
     for hp in hbuf:
         _lib.check(lib.spn_host_free(hp), "host_free")
 
@@ -513,7 +542,11 @@ def run_b200(args):
                      "traffic": measured_traffic("bs8_gather_scatter_64_p7") if (world == 1 and nx == 64 and p == 7) else None},
         "e2e": {"value": Ng / t_e2e * 1e-9, "unit": "GDOF/s", "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
                 "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
-                "api": "ogs_t::GatherScatterStart/Finish(pinned host q): H2D -> GatherScatter -> D2H per step, two vectors in flight"},
+                "api": "ogs_t::GatherScatterStart/Finish(pinned host q): H2D -> GatherScatter -> D2H per step, two vectors in flight",
+                "copy_ceiling": {"ms_per_step": t_copy * 1e3, "GDOF/s": Ng / t_copy * 1e-9,
+                                 "gbs_per_gpu_per_direction": nbytes / t_copy * 1e-9,
+                                 "what": "the same H2D + D2H of one step on two streams with no kernel, max over ranks (host wall clock)",
+                                 "e2e_fraction_of_ceiling": t_copy / t_e2e}},
         "gpu_launches": args.steps * launches_per_step,
         "clocks": clocks,
         "parity_checked": parity["ok"], "parity": parity,

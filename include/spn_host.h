@@ -64,7 +64,7 @@ int spn_host_ogs_exchange_info(spn_host_ogs_t ogs, int mode, long long* info);
  *  0 local rowStartsT  1 local colIdsT  2 local rowStartsN  3 local colIdsN
  *  4 halo  rowStartsT  5 halo  colIdsT  6 halo  rowStartsN  7 halo  colIdsN
  *  per mode: 8 sendIds 9 sendRanks 10 sendCounts 11 sendOffsets 12 recvRanks 13 recvCounts 14 recvOffsets
- *           15 cmbStarts 16 cmbIds 17 recvRows */
+ *           15 cmbStarts 16 cmbIds 17 recvRows 18 rowSendStarts 19 rowSendDst 20 slotDst (peer-memory pack: send slots per halo row) */
 int spn_host_ogs_array(spn_host_ogs_t ogs, int which, int mode, const int** ptr, long long* len);
 int spn_host_ogs_halo_labels(spn_host_ogs_t ogs, const long long** ptr, long long* len);  /* |label| of every halo row */
 

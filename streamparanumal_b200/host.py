@@ -161,7 +161,7 @@ def rank_grid(rank, size):
 _ARRAYS = {"local_rowStartsT": 0, "local_colIdsT": 1, "local_rowStartsN": 2, "local_colIdsN": 3,
            "halo_rowStartsT": 4, "halo_colIdsT": 5, "halo_rowStartsN": 6, "halo_colIdsN": 7,
            "sendIds": 8, "sendRanks": 9, "sendCounts": 10, "sendOffsets": 11, "recvRanks": 12, "recvCounts": 13,
-           "recvOffsets": 14, "cmbStarts": 15, "cmbIds": 16, "recvRows": 17}
+           "recvOffsets": 14, "cmbStarts": 15, "cmbIds": 16, "recvRows": 17, "rowSendStarts": 18, "rowSendDst": 19, "slotDst": 20}
 
 
 class Ogs:

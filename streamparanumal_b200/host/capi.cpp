@@ -161,6 +161,9 @@ int spn_host_ogs_array(spn_host_ogs_t h, int which, int mode, const int** ptr, l
     case 15: v = &d.cmbStarts; break;
     case 16: v = &d.cmbIds; break;
     case 17: v = &d.recvRows; break;
+    case 18: v = &d.rowSendStarts; break;
+    case 19: v = &d.rowSendDst; break;
+    case 20: v = &d.slotDst; break;
     default: return SPN_ERR_INVALID_ARGUMENT;
   }
   *ptr = v->data();

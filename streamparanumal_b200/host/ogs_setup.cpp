@@ -10,6 +10,7 @@
 //      receiver agree on the message layout without exchanging row indices (the reference ships
 //      remote row ids through four more alltoallv rounds: ogsSetup.cpp:617-813).
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -73,10 +74,80 @@ struct Key {
   hlong label;  // |label|
   dlong idx;    // position in the entry list
 };
-inline bool key_less(const Key& a, const Key& b) { return a.label < b.label || (a.label == b.label && a.idx < b.idx); }
+
+// Stable parallel LSD radix sort of keys[i] = {label, i} by label (11-bit digits, as many passes as the largest label
+// needs).  Stable + the initial order i ascending means equal labels stay in ascending position: the (label, idx) order
+// the grouping below relies on.  Replaces a comparison sort of 2^27 16-byte keys (3-5 s of the setup) by 3 streaming passes.
+void sort_keys_by_label(std::vector<Key>& keys) {
+  const size_t n = keys.size();
+  if (n < 2) return;
+  hlong maxLabel = 0;
+#pragma omp parallel for reduction(max : maxLabel)
+  for (size_t i = 0; i < n; ++i) maxLabel = std::max(maxLabel, keys[i].label);
+  constexpr int BITS = 11, BUCKETS = 1 << BITS;
+  int passes = 1;
+  while (passes * BITS < 63 && (maxLabel >> (passes * BITS)) != 0) ++passes;
+  std::vector<Key> tmp(n);
+  Key* src = keys.data();
+  Key* dst = tmp.data();
+  const int T = omp_get_max_threads();
+  std::vector<size_t> hist((size_t)T * BUCKETS);
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = pass * BITS;
+#pragma omp parallel num_threads(T)
+    {
+      const int t = omp_get_thread_num();
+      const size_t lo = n * (size_t)t / T, hi = n * (size_t)(t + 1) / T;
+      size_t* h = hist.data() + (size_t)t * BUCKETS;
+      std::fill(h, h + BUCKETS, 0);
+      for (size_t i = lo; i < hi; ++i) h[(src[i].label >> shift) & (BUCKETS - 1)]++;
+#pragma omp barrier
+#pragma omp single
+      {
+        size_t run = 0;  // bucket-major, thread-minor: thread t's share of bucket b starts after the lower threads' shares
+        for (int b2 = 0; b2 < BUCKETS; ++b2)
+          for (int t2 = 0; t2 < T; ++t2) {
+            const size_t c = hist[(size_t)t2 * BUCKETS + b2];
+            hist[(size_t)t2 * BUCKETS + b2] = run;
+            run += c;
+          }
+      }
+      for (size_t i = lo; i < hi; ++i) dst[h[(src[i].label >> shift) & (BUCKETS - 1)]++] = src[i];
+    }
+    std::swap(src, dst);
+  }
+  if (src != keys.data()) keys.swap(tmp);
+}
+
+// exclusive prefix sum of v[0..n) in place, returns the total (parallel two-pass)
+template <typename T>
+T exclusive_scan(T* v, size_t n) {
+  const int P = omp_get_max_threads();
+  std::vector<T> part((size_t)P + 1, 0);
+#pragma omp parallel num_threads(P)
+  {
+    const int t = omp_get_thread_num();
+    const size_t lo = n * (size_t)t / P, hi = n * (size_t)(t + 1) / P;
+    T s = 0;
+    for (size_t i = lo; i < hi; ++i) s += v[i];
+    part[t + 1] = s;
+#pragma omp barrier
+#pragma omp single
+    for (int q = 0; q < P; ++q) part[q + 1] += part[q];
+    T run = part[t];
+    for (size_t i = lo; i < hi; ++i) {
+      const T x = v[i];
+      v[i] = run;
+      run += x;
+    }
+  }
+  return part[P];
+}
 
 // Number the label groups of one entry set and build both CSR variants.
 // entries: signed labels `ids` at columns `cols` (cols strictly ascending).
+// Rows = label groups in first-appearance order, groups with a positive copy first (libs/ogs/ogsSetup.cpp:492-559);
+// columns ascend inside a row (stable SortByRow, :561-579).  Every pass is a parallel loop or a prefix sum.
 std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const std::vector<hlong>& ids,
                                               const std::vector<dlong>& cols) {
   auto op = std::make_shared<ogsOperator_t>();
@@ -88,74 +159,85 @@ std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const std:
   std::vector<Key> keys((size_t)n);
 #pragma omp parallel for
   for (dlong i = 0; i < n; ++i) keys[i] = Key{habs(ids[i]), i};
-  __gnu_parallel::sort(keys.begin(), keys.end(), key_less);
+  sort_keys_by_label(keys);  // groups contiguous, members in ascending entry (= column) order
 
-  // group heads in sorted order
-  std::vector<dlong> groupOfSorted((size_t)n);
-  dlong NT = 0;
-  for (dlong i = 0; i < n; ++i) {
-    if (i == 0 || keys[i].label != keys[i - 1].label) ++NT;
-    groupOfSorted[i] = NT - 1;
-  }
-  std::vector<dlong> groupFirst((size_t)NT);  // entry index of the first appearance of each group
+  // group starts in sorted order
+  std::vector<dlong> groupOfSorted((size_t)n);  // first: 1 at a group start, then the group index
+#pragma omp parallel for
+  for (dlong i = 0; i < n; ++i) groupOfSorted[i] = (i == 0 || keys[i].label != keys[i - 1].label) ? 1 : 0;
+  const dlong NT = n ? exclusive_scan(groupOfSorted.data(), (size_t)n) : 0;  // groupOfSorted[i] = groups before i ...
+#pragma omp parallel for
+  for (dlong i = 0; i < n; ++i)  // ... make it the group OF i: a start belongs to the group it opens
+    if (i == 0 || keys[i].label != keys[i - 1].label) groupOfSorted[i] += 1;
+#pragma omp parallel for
+  for (dlong i = 0; i < n; ++i) groupOfSorted[i] -= 1;
+  std::vector<dlong> groupStart((size_t)NT + 1);  // sorted position of the first member
+#pragma omp parallel for
+  for (dlong i = 0; i < n; ++i)
+    if (i == 0 || groupOfSorted[i] != groupOfSorted[i - 1]) groupStart[groupOfSorted[i]] = i;
+  groupStart[NT] = n;
   std::vector<char> groupPos((size_t)NT, 0);  // has a positive copy on this rank
-  for (dlong i = 0; i < n; ++i) {
-    const dlong g = groupOfSorted[i];
-    if (i == 0 || groupOfSorted[i - 1] != g) groupFirst[g] = keys[i].idx;  // smallest idx: sorted by (label, idx)
-    if (ids[keys[i].idx] > 0) groupPos[g] = 1;
+#pragma omp parallel for
+  for (dlong g = 0; g < NT; ++g) {
+    char pos = 0;
+    for (dlong i = groupStart[g]; i < groupStart[g + 1]; ++i) pos |= (ids[keys[i].idx] > 0) ? 1 : 0;
+    groupPos[g] = pos;
   }
-  // first-appearance order, positive groups first (libs/ogs/ogsSetup.cpp:492-559)
-  std::vector<dlong> headGroup((size_t)n, -1);
-  for (dlong g = 0; g < NT; ++g) headGroup[groupFirst[g]] = g;
+  // first-appearance order, positive groups first: flags in ENTRY order at each group's first member, two prefix sums
+  std::vector<dlong> headP((size_t)n, 0), headM((size_t)n, 0);
+#pragma omp parallel for
+  for (dlong g = 0; g < NT; ++g) {
+    const dlong first = keys[groupStart[g]].idx;  // smallest entry index of the group
+    if (groupPos[g]) headP[first] = 1; else headM[first] = 1;
+  }
+  const dlong NP = n ? exclusive_scan(headP.data(), (size_t)n) : 0;
+  if (n) exclusive_scan(headM.data(), (size_t)n);
   std::vector<dlong> rowOfGroup((size_t)NT);
-  dlong NP = 0;
-  for (dlong g = 0; g < NT; ++g) NP += groupPos[g] ? 1 : 0;
-  dlong nextP = 0, nextM = NP;
-  for (dlong i = 0; i < n; ++i) {
-    const dlong g = headGroup[i];
-    if (g < 0) continue;
-    rowOfGroup[g] = groupPos[g] ? nextP++ : nextM++;
+#pragma omp parallel for
+  for (dlong g = 0; g < NT; ++g) {
+    const dlong first = keys[groupStart[g]].idx;
+    rowOfGroup[g] = groupPos[g] ? headP[first] : NP + headM[first];
   }
-  headGroup.clear();
-  headGroup.shrink_to_fit();
+  headP.clear(); headP.shrink_to_fit();
+  headM.clear(); headM.shrink_to_fit();
   op->NrowsT = NT;
   op->NrowsN = NP;
 
-  std::vector<dlong> rowOfEntry((size_t)n);
+  // CSR "T": every copy.  Row lengths = group sizes; members of a group are already in ascending column order.
   op->rowLabel.assign((size_t)NT, 0);
-#pragma omp parallel for
-  for (dlong i = 0; i < n; ++i) {
-    const dlong row = rowOfGroup[groupOfSorted[i]];
-    rowOfEntry[keys[i].idx] = row;
-    op->rowLabel[row] = keys[i].label;  // same value from every copy
-  }
-  keys.clear();
-  keys.shrink_to_fit();
-  groupOfSorted.clear();
-  groupOfSorted.shrink_to_fit();
-
-  // CSR "T": every copy; sweeping entries in column order keeps columns ascending inside a row
   op->rowStartsT.assign((size_t)NT + 1, 0);
-  for (dlong i = 0; i < n; ++i) op->rowStartsT[rowOfEntry[i] + 1]++;
-  for (dlong r = 0; r < NT; ++r) op->rowStartsT[r + 1] += op->rowStartsT[r];
+#pragma omp parallel for
+  for (dlong g = 0; g < NT; ++g) {
+    const dlong row = rowOfGroup[g];
+    op->rowStartsT[row] = groupStart[g + 1] - groupStart[g];
+    op->rowLabel[row] = keys[groupStart[g]].label;
+  }
+  if (NT) exclusive_scan(op->rowStartsT.data(), (size_t)NT + 1);
   op->colIdsT.resize((size_t)n);
-  {
-    std::vector<dlong> fill(op->rowStartsT.begin(), op->rowStartsT.end() - 1);
-    for (dlong i = 0; i < n; ++i) op->colIdsT[fill[rowOfEntry[i]]++] = cols[i];
+#pragma omp parallel for
+  for (dlong g = 0; g < NT; ++g) {
+    dlong o = op->rowStartsT[rowOfGroup[g]];
+    for (dlong i = groupStart[g]; i < groupStart[g + 1]; ++i) op->colIdsT[o++] = cols[keys[i].idx];
   }
   // CSR "N": positive copies only (libs/ogs/ogsOperator.cpp:620-643).  rowStartsN carries NrowsT+1
   // entries (rows >= NrowsN are empty) so kernels may walk the T row partition over it.
   if (op->kind == Signed) {
     op->rowStartsN.assign((size_t)NT + 1, 0);
-    dlong nnzN = 0;
-    for (dlong i = 0; i < n; ++i)
-      if (ids[i] > 0) { op->rowStartsN[rowOfEntry[i] + 1]++; ++nnzN; }
-    for (dlong r = 0; r < NT; ++r) op->rowStartsN[r + 1] += op->rowStartsN[r];
+#pragma omp parallel for
+    for (dlong g = 0; g < NT; ++g) {
+      dlong c = 0;
+      for (dlong i = groupStart[g]; i < groupStart[g + 1]; ++i) c += (ids[keys[i].idx] > 0) ? 1 : 0;
+      op->rowStartsN[rowOfGroup[g]] = c;
+    }
+    const dlong nnzN = NT ? exclusive_scan(op->rowStartsN.data(), (size_t)NT + 1) : 0;
     op->nnzN = nnzN;
     op->colIdsN.resize((size_t)nnzN);
-    std::vector<dlong> fill(op->rowStartsN.begin(), op->rowStartsN.end() - 1);
-    for (dlong i = 0; i < n; ++i)
-      if (ids[i] > 0) op->colIdsN[fill[rowOfEntry[i]]++] = cols[i];
+#pragma omp parallel for
+    for (dlong g = 0; g < NT; ++g) {
+      dlong o = op->rowStartsN[rowOfGroup[g]];
+      for (dlong i = groupStart[g]; i < groupStart[g + 1]; ++i)
+        if (ids[keys[i].idx] > 0) op->colIdsN[o++] = cols[keys[i].idx];
+    }
   } else {
     op->nnzN = op->nnzT;
     op->NrowsN = op->NrowsT;
@@ -232,6 +314,9 @@ void ogs_t::SetupPeerExchange() {
   SPN_ABORT("peer exchange: more ranks than SPN_P2P_MAX_RANKS", size > SPN_P2P_MAX_RANKS);
   dlong maxRecv = 0;
   for (int m = 0; m < 3; ++m) maxRecv = std::max(maxRecv, data[m].Nrecv);
+  // every rank lays its block out the same way: a sender computes the address of a destination's second half from the
+  // common half size (ranks with different receive counts would otherwise disagree on where half 1 starts)
+  comm.Allreduce(maxRecv, Comm::Max);
   auto align = [](size_t b) { return (b + 255) / 256 * 256; };
   p2p.flagBytes = align(2 * sizeof(unsigned long long) * (size_t)size);  // flags, then acks
   p2p.halfBytes = align(kPeerEntryBytes * (size_t)std::max<dlong>(maxRecv, 1));
@@ -390,8 +475,23 @@ struct SetupThreads {
 };
 }  // namespace
 
+namespace {
+struct PhaseTimer {  // SPN_SETUP_TIMING=1: seconds per phase of SetupPlan on rank 0
+  bool on;
+  timePoint_t t;
+  PhaseTimer(int rank) : on(rank == 0 && getenv("SPN_SETUP_TIMING") != nullptr), t(Time()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    const timePoint_t n = Time();
+    fprintf(stderr, "  ogs setup: %-38s %7.3f s\n", what, std::chrono::duration<double>(n - t).count());
+    t = n;
+  }
+};
+}  // namespace
+
 void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_, const bool unique_, const bool verbose) {
   SetupThreads threads(comm_.size());
+  PhaseTimer phase(comm_.rank());
   N = N_;
   comm = comm_;
   kind = kind_;
@@ -414,6 +514,7 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
       if (ids[n] != 0) { colIds[c] = n; baseIds[c] = ids[n]; ++c; }
   }
 
+  phase.lap("non-zero labels");
   // ---- 1. directory round ------------------------------------------------------------------
   std::vector<int> sendCounts(size, 0), sendOffsets(size + 1, 0), recvCounts(size, 0), recvOffsets(size + 1, 0);
   for (dlong n = 0; n < Nids; ++n) sendCounts[habs(baseIds[n]) % size]++;
@@ -435,11 +536,13 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   comm.Alltoallv(sendLabels.data(), sendCounts.data(), sendOffsets.data(), recvLabels.data(), recvCounts.data(),
                  recvOffsets.data());
 
+  phase.lap("route labels to directory ranks");
   // group the received copies by |label|; inside a group they stay in (source rank, source order)
   std::vector<Key> keys((size_t)recvN);
 #pragma omp parallel for
   for (dlong i = 0; i < recvN; ++i) keys[i] = Key{habs(recvLabels[i]), i};
-  __gnu_parallel::sort(keys.begin(), keys.end(), key_less);
+  sort_keys_by_label(keys);
+  phase.lap("sort received labels");
   auto rank_of = [&](dlong idx) {  // source rank of receive slot idx
     return (int)(std::upper_bound(recvOffsets.begin(), recvOffsets.end(), (int)idx) - recvOffsets.begin()) - 1;
   };
@@ -502,6 +605,7 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   keys.clear();
   keys.shrink_to_fit();
 
+  phase.lap("groups: shared / pick");
   comm.Allreduce(is_unique, Comm::Min);
   gather_defined = (is_unique == 1);
   // libs/ogs/ogsSetup.cpp:405-408
@@ -545,6 +649,7 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
     comm.Alltoallv(flat.data(), sc.data(), so.data(), sharerStream.data(), rc.data(), ro.data());
   }
 
+  phase.lap("answers back to the sources");
   // ---- 2. split into local / halo entries and number the rows ---------------------------------
   std::vector<hlong> localIds, haloIds;
   std::vector<dlong> localCols, haloCols;
@@ -552,7 +657,9 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
     if (sharedOfSlot[sendPos[n]]) { haloIds.push_back(baseIds[n]); haloCols.push_back(colIds[n]); }
     else { localIds.push_back(baseIds[n]); localCols.push_back(colIds[n]); }
   }
+  phase.lap("split local / halo");
   gatherLocal = build_operator(kind, N, localIds, localCols);
+  phase.lap("local operator");
   gatherHalo = build_operator(kind, N, haloIds, haloCols);
   NlocalT = gatherLocal->NrowsT;
   NlocalP = gatherLocal->NrowsN;
@@ -562,6 +669,7 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   NgatherGlobal = Ngather;
   comm.Allreduce(NgatherGlobal);
 
+  phase.lap("halo operator");
   // ---- 3. exchange plan -------------------------------------------------------------------------
   // halo row of a label: rowLabel sorted once
   std::vector<std::pair<hlong, dlong>> labelRow((size_t)NhaloT);
@@ -656,6 +764,7 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
     std::vector<dlong> fill2(d.rowSendStarts.begin(), d.rowSendStarts.end() - 1);
     for (dlong i = 0; i < d.Nsend; ++i) d.rowSendDst[fill2[d.sendIds[i]]++] = d.slotDst[i];
   }
+  phase.lap("exchange plan");
 }
 
 }  // namespace ogs

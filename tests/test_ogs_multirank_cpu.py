@@ -51,6 +51,16 @@ def _worker(rank, world, port, tmpdir, nx, ny, nz, p, K, dtype_name, kind_unique
             assert comm.allreduce(int((ids > 0).sum())) == nglobal  # exactly one positive copy per label
         sym = plan.mode[host.SYM]
         assert sym["Nsend"] == sym["Nrecv"]  # Sym: every sharer sends to and hears from every other sharer
+        # peer-memory pack tables: the send slots listed per halo row are exactly the slots whose row it is
+        for m in (host.SYM, host.NOTRANS, host.TRANS):
+            d = plan.mode[m]
+            rss, rsd, sd = ogs.array("rowSendStarts", m), ogs.array("rowSendDst", m), ogs.array("slotDst", m)
+            assert sd.size == d["Nsend"] and rsd.size == d["Nsend"] and (ogs.NhaloT == 0 or rss.size == ogs.NhaloT + 1)
+            for p_, (c, o) in enumerate(zip(d["sendCounts"], d["sendOffsets"])):
+                assert np.array_equal(sd[o:o + c], (p_ << 24) | np.arange(c))
+            for row in range(ogs.NhaloT):
+                mine = sorted(rsd[rss[row]:rss[row + 1]].tolist())
+                assert mine == sorted(sd[np.flatnonzero(d["sendIds"] == row)].tolist())
 
         # ---- values --------------------------------------------------------------------------------
         if np.issubdtype(dtype, np.floating):
