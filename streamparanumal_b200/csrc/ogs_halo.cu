@@ -74,23 +74,25 @@ __device__ __forceinline__ unsigned long long p2p_begin_send(const spn_p2p_plan_
 }
 
 // End of a sending launch, after every thread has issued its peer stores: the last block raises the flags and advances
-// the state.  stores -> fence.sys -> block barrier -> counter (gpu scope) ... last block: fence.sys -> release stores.
+// the state.  stores -> fence.sys -> block barrier -> counter (gpu scope) ... last block: fence.sys -> release stores,
+// one destination per thread (a single thread storing to 7 peers one after the other costs a fabric round trip each).
 __device__ __forceinline__ void p2p_end_send(const spn_p2p_plan_t* __restrict__ plan, spn_p2p_state_t* state, unsigned long long e) {
+  __shared__ int s_last;
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int old = atomicInc(&state->packCounter, gridDim.x - 1);  // wraps to 0 after the last block: re-armed
-    if (old == gridDim.x - 1) {
-      __threadfence_system();
-      const int h = (int)(e & 1ull);
-      for (int i = 0; i < plan->nsend; ++i) {
-        st_release_sys(plan->flagRemote[i], e);
-        state->lastSend[plan->dstRank[i]][h] = e;
-      }
-      state->epoch = e;
-      __threadfence();
-    }
+    s_last = (old == gridDim.x - 1);
   }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  const int h = (int)(e & 1ull);
+  if ((int)threadIdx.x < plan->nsend) {
+    st_release_sys(plan->flagRemote[threadIdx.x], e);
+    state->lastSend[plan->dstRank[threadIdx.x]][h] = e;
+  }
+  if (threadIdx.x == 0) state->epoch = e;
 }
 
 // one thread per (halo row, k): fold once, keep the partial in ownBuf, fan it out to the row's send slots
@@ -173,15 +175,18 @@ halo_combine_scatter_kernel(int Nrows, int NrowsP, int K, const int* __restrict_
     }
   }
   if (P2P) {
-    // every block has read its part of the receive half: the last one acknowledges the sources
+    // every block has read its part of the receive half: the last one acknowledges the sources, one per thread
+    __shared__ int s_last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
       const unsigned int old = atomicInc(&state->combineCounter, gridDim.x - 1);
-      if (old == gridDim.x - 1) {
-        __threadfence_system();
-        for (int i2 = 0; i2 < plan->nrecv; ++i2) st_release_sys(plan->ackRemote[i2], e);
-      }
+      s_last = (old == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < plan->nrecv) {
+      __threadfence_system();
+      st_release_sys(plan->ackRemote[threadIdx.x], e);
     }
   }
 }

@@ -202,10 +202,10 @@ void ogs_t::GatherScatter(void* o_v, int k, Type type, Op op, Transpose trans) {
     use_graphs = (e && e[0] == '0') ? 0 : 1;
   }
   const size_t Nbytes = (size_t)k * Sizeof(type);
-  // replay pays off where the call is launch-bound; above ~16 M entries per rank the directly issued sequence is as fast
-  // or faster (measured at 2 ranks: 64^3/2 elements per rank 0.263 ms direct vs 0.274 ms replayed; 16^3: 39.7 vs 30.2 us)
+  // replay pays off where the call is launch-bound; from ~16 M entries per rank on the directly issued sequence is faster
+  // (8 ranks: 16^3 elements per rank 54 us replayed vs 63 us direct, 32^3 109 vs 92 us; 2 ranks: 64^3/2 0.274 vs 0.263 ms)
   const bool graphable = use_graphs && comm.size() > 1 && UsePeerExchange(Nbytes) && !exchange_in_flight && !peer_exchange_in_flight &&
-                         (size_t)N * (size_t)k <= ((size_t)1 << 24);
+                         (size_t)N * (size_t)k <= ((size_t)1 << 23);
   if (!graphable) {
     GatherScatterStart(o_v, k, type, op, trans);
     GatherScatterFinish(o_v, k, type, op, trans);
