@@ -1,9 +1,10 @@
 /* mpi.h — stand-in for the MPI calls streamParanumal's first-party code makes (reference: include/comm.hpp:30-575,
  * libs/core/comm.cpp:34-120; full symbol list: grep -rhoE '\bMPI_[A-Za-z_]+' include libs BS).  This image has no MPI.
  * With `-I include/shim` the reference's comm_t compiles unchanged against this header; the functions live in
- * streamparanumal_b200/shim/mpi_shim.cpp.  That implementation runs ONE rank per process group (`mpirun -np 1`):
- * every collective is the single-rank identity, point-to-point messages to self are matched by (communicator, tag) in
- * posting order.  Multi-rank runs of the native path use spn::comm_t (Unix sockets + NCCL), not this header.
+ * streamparanumal_b200/shim/mpi_shim.cpp: the ranks of ONE node, started by `spnrun -np P <exe>` (the mpirun stand-in, which
+ * sets SPN_RANK / SPN_SIZE / SPN_RENDEZVOUS), talk over a mesh of Unix-domain sockets; with no launcher the process is rank 0
+ * of 1.  Host buffers only.  Point-to-point messages match by (communicator, source, tag) in arrival order; collectives are
+ * built on them and reduce in rank order.
  */
 #ifndef SPN_SHIM_MPI_H
 #define SPN_SHIM_MPI_H

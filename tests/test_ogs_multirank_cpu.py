@@ -49,6 +49,11 @@ def _worker(rank, world, port, tmpdir, nx, ny, nz, p, K, dtype_name, kind_unique
         if kind == host.SIGNED:
             assert tot == nglobal == ogs.NgatherGlobal
             assert comm.allreduce(int((ids > 0).sum())) == nglobal  # exactly one positive copy per label
+            if unique:
+                # ... and it is the copy the reference's rule picks (rank-seeded LCG on the directory rank)
+                everyone = [None] * world
+                dist.all_gather_object(everyone, np.abs(ids))
+                assert np.array_equal(ids > 0, reference_positive_pick(everyone, world)[rank]), "positive copies differ from the reference's rule"
         sym = plan.mode[host.SYM]
         assert sym["Nsend"] == sym["Nrecv"]  # Sym: every sharer sends to and hears from every other sharer
         # peer-memory pack tables: the send slots listed per halo row are exactly the slots whose row it is
@@ -125,6 +130,35 @@ def _worker(rank, world, port, tmpdir, nx, ny, nz, p, K, dtype_name, kind_unique
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def reference_positive_pick(all_abs_ids, world):
+    """The reference's choice of the positive copy of every label, restated from libs/ogs/ogsSetup.cpp:292-382 and
+    libs/primitives/random.cpp:45-164: every non-zero label travels to directory rank |label| % P, which receives them
+    in (source rank, source order), groups them by label in ascending label order and keeps, for its n-th group, member
+    rands[n] % size — rands[n] = |int32(X_n)|, X_0 = a * (~0 ^ rank) + c, X_(n+1) = a * X_n + c (mod 2^64) — with the
+    members of a group in arrival order (the stable instance of the reference's unstable sort).
+    Returns, per rank, a boolean array: entry is the positive copy."""
+    A, C, M = 6364136223846793005, 1, (1 << 64) - 1
+    positive = [np.zeros(len(a), dtype=bool) for a in all_abs_ids]
+    for d in range(world):
+        lab, src, pos = [], [], []
+        for r in range(world):
+            idx = np.flatnonzero((all_abs_ids[r] != 0) & (all_abs_ids[r] % world == d))
+            lab.append(all_abs_ids[r][idx]); src.append(np.full(idx.size, r)); pos.append(idx)
+        lab, src, pos = np.concatenate(lab), np.concatenate(src), np.concatenate(pos)
+        order = np.argsort(lab, kind="stable")
+        lab, src, pos = lab[order], src[order], pos[order]
+        starts = np.flatnonzero(np.r_[True, lab[1:] != lab[:-1]]) if lab.size else np.zeros(0, dtype=np.int64)
+        ends = np.r_[starts[1:], lab.size]
+        x = (A * (M ^ d) + C) & M
+        for s, e in zip(starts, ends):
+            v = x & 0xffffffff
+            v = v - (1 << 32) if v >= (1 << 31) else v   # int32(x)
+            m = abs(v) % (e - s)
+            positive[src[s + m]][pos[s + m]] = True
+            x = (A * x + C) & M
+    return positive
 
 
 def _free_port():
