@@ -167,6 +167,31 @@ int ref_ogs_gather_scatter_device(void* handle, void* v, int k, int type, int op
   return 0;
 }
 
+// ---- halo_t (include/ogs.hpp:347-397, libs/ogs/ogsHalo.cpp): ids > 0 the owned copy, ids < 0 halo copies ----------------
+struct HaloHandle {
+  ogs::halo_t halo;
+  memory<hlong> ids;
+};
+void* ref_halo_create(int N, const long long* ids, int verbose) {
+  HaloHandle* h = new HaloHandle();
+  h->ids = memory<hlong>(N);
+  memcpy(h->ids.ptr(), ids, sizeof(hlong) * (size_t)N);
+  h->halo.Setup(N, h->ids, env().comm, ogs::Pairwise, verbose != 0, env().platform);
+  return h;
+}
+void ref_halo_destroy(void* handle) { delete static_cast<HaloHandle*>(handle); }
+int ref_halo_nhalo(void* handle) { return static_cast<HaloHandle*>(handle)->halo.Nhalo; }
+// host-memory Exchange (op 0) / Combine (op 1) of v (N*k entries) in place
+int ref_halo_apply(void* handle, int which, void* v, int k, int type) {
+  HaloHandle* h = static_cast<HaloHandle*>(handle);
+  const size_t n = (size_t)h->halo.N * k;
+  BY_TYPE(type, with_host<T>(v, n, [&](memory<T>& m) {
+    if (which == 0) h->halo.Exchange(m, k);
+    else h->halo.Combine(m, k);
+  }));
+  return 0;
+}
+
 // Times `steps` calls of the reference's own BS8 operation, mesh.ogs.GatherScatter(q, 1, ogs::Add, ogs::Sym)
 // (BS/BS8/src/bs8Run.cpp:47-57), after `warmup` calls, on FP64 data resident in the reference's own containers:
 //   path 0: the host-memory overload (memory<dfloat>; libs/ogs/ogs.cpp:127-204 -> the OpenMP-threaded host operator,

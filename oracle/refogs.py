@@ -38,6 +38,11 @@ def lib():
         l.ref_ogs_scatter.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]
         l.ref_ogs_time_gather_scatter.restype = ctypes.c_double
         l.ref_ogs_time_gather_scatter.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_int)]
+        l.ref_halo_create.restype = c_void_p
+        l.ref_halo_create.argtypes = [c_int, c_void_p, c_int]
+        l.ref_halo_destroy.argtypes = [c_void_p]
+        l.ref_halo_nhalo.argtypes = [c_void_p]
+        l.ref_halo_apply.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int]
         l.ref_mesh_box_hex_ids.restype = c_longlong
         l.ref_mesh_box_hex_ids.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_longlong]
         _lib = l
@@ -114,6 +119,31 @@ class RefOgs:
             self.close()
         except Exception:
             pass
+
+
+class RefHalo:
+    """libp::ogs::halo_t::Setup(N, ids, comm, Pairwise, verbose, platform(Serial)) and its host-memory Exchange / Combine"""
+
+    def __init__(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        self._h = lib().ref_halo_create(ids.size, ids.ctypes.data, 0)
+        self.Nhalo = lib().ref_halo_nhalo(self._h)
+
+    def _apply(self, which, v, k):
+        v = np.ascontiguousarray(v).copy()
+        assert lib().ref_halo_apply(self._h, which, v.ctypes.data, k, _TYPES[v.dtype]) == 0
+        return v
+
+    def exchange(self, v, k=1):
+        return self._apply(0, v, k)
+
+    def combine(self, v, k=1):
+        return self._apply(1, v, k)
+
+    def close(self):
+        if self._h:
+            lib().ref_halo_destroy(self._h)
+            self._h = None
 
 
 def mesh_box_hex_ids(nx, ny, nz, p):

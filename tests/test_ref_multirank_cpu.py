@@ -56,6 +56,16 @@ def _worker(rank, world, port, tmpdir, nx, ny, nz, p):
             exp = ref.gather_scatter(v, 1, refogs.ADD, trans)          # MPI messages between the P reference ranks
             got = ogs_sim.gather_scatter(plan, v, K=1, op=host.ADD, trans=trans)
             assert np.array_equal(got.view(np.int64), exp.view(np.int64)), f"GatherScatter({tname}) differs from the reference's"
+        # vector-valued fields, the other element types and reduction ops
+        for K, dt, op in ((3, np.float32, refogs.MAX), (2, np.int64, refogs.ADD), (2, np.int32, refogs.MIN), (3, np.float64, refogs.MUL)):
+            if np.issubdtype(dt, np.floating):
+                w = util.splitmix64(ids.size * K, 900 + rank).astype(dt)
+            else:
+                w = ((np.arange(ids.size * K, dtype=np.int64) * 7919 + rank) % 23 - 11).astype(dt)
+            for trans in (host.SYM, host.TRANS):
+                exp = ref.gather_scatter(w, K, op, trans)
+                got = ogs_sim.gather_scatter(plan, w, K=K, op=op, trans=trans)
+                assert np.array_equal(got.view(np.uint8), exp.view(np.uint8)), f"GatherScatter K={K} {dt.__name__} op={op} trans={trans}"
         gv_ref = ref.gather(v, 1, refogs.ADD, refogs.TRANS)[: ref.Ngather]
         gv = ogs_sim.gather(plan, v, K=1, op=host.ADD, trans=host.TRANS)
         assert np.array_equal(gv[: ogs.Ngather].view(np.int64), gv_ref.view(np.int64)), "Gather(Trans) differs from the reference's"
@@ -66,6 +76,41 @@ def _worker(rank, world, port, tmpdir, nx, ny, nz, p):
         dist.barrier()
         ref.close()
         ogs.close()
+        comm.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _halo_worker(rank, world, port, tmpdir, K, dtype_name):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SPN_RANK=str(rank), SPN_SIZE=str(world),
+                      SPN_RENDEZVOUS=tmpdir, OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ogs_sim
+        import test_halo_cpu
+        import spn_testutil as util
+        from oracle import refogs
+        from streamparanumal_b200 import host
+        dtype = np.dtype(dtype_name)
+        comm = host.Comm(rank, world, rendezvous=tmpdir)
+        ids = test_halo_cpu._ids(rank, world)
+        ref = refogs.RefHalo(ids)                     # the reference's halo_t as rank `rank` of `world`
+        halo = host.Ogs(ids.copy(), comm, kind=host.HALO, unique=False)
+        assert halo.NhaloT - halo.NhaloP == ref.Nhalo
+        plan = ogs_sim.Plan(halo)
+        if np.issubdtype(dtype, np.floating):
+            v = util.splitmix64(ids.size * K, 700 + rank).astype(dtype)
+        else:
+            v = ((np.arange(ids.size * K, dtype=np.int64) * 7919 + rank) % 23 - 11).astype(dtype)
+        got = ogs_sim.gather_scatter(plan, v, K=K, op=host.ADD, trans=host.NOTRANS)
+        assert np.array_equal(got.view(np.uint8), ref.exchange(v, K).view(np.uint8)), "halo_t::Exchange differs from the reference's"
+        got = ogs_sim.gather_scatter(plan, v, K=K, op=host.ADD, trans=host.TRANS)
+        assert np.array_equal(got.view(np.uint8), ref.combine(v, K).view(np.uint8)), "halo_t::Combine differs from the reference's"
+        dist.barrier()
+        ref.close()
+        halo.close()
         comm.close()
     finally:
         dist.destroy_process_group()
@@ -85,3 +130,13 @@ def test_native_plan_equals_reference_ogs_at_p_ranks(world, nx, ny, nz, p):
         pytest.skip("oracle/_ref/libref_ogs.so not built here (needs /root/reference)")
     with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
         mp.spawn(_worker, args=(world, _free_port(), tmpdir, nx, ny, nz, p), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("world,K,dtype", [(2, 1, "float64"), (3, 2, "float64"), (4, 1, "int32"), (3, 3, "float32")])
+def test_native_halo_equals_reference_halo_t(world, K, dtype):
+    """halo_t::Exchange / Combine (libs/ogs/ogsHalo.cpp) of the reference, P real processes, against the native Kind-Halo plan"""
+    from oracle import refogs
+    if not refogs.available():
+        pytest.skip("oracle/_ref/libref_ogs.so not built here (needs /root/reference)")
+    with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
+        mp.spawn(_halo_worker, args=(world, _free_port(), tmpdir, K, dtype), nprocs=world, join=True)

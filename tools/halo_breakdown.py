@@ -1,5 +1,7 @@
 """Where does a multi-rank BS8 step spend its time?  Run under torch.distributed.run with N ranks:
-times ogs_t::GatherScatter with phases switched off (spn_host_debug_set: 1 pack/send, 2 interior, 4 combine)."""
+times ogs_t::GatherScatter with phases switched off (spn_host_debug_set: 1 pack/send, 2 interior, 4 combine).
+Needs a host library built with the probes compiled in:  make -B CXXFLAGS+=-DSPN_TIMING_PROBES streamparanumal_b200/lib/libspn_host.so
+(the shipped library compiles them away: results are wrong with a phase skipped)."""
 import os
 import sys
 
