@@ -76,7 +76,7 @@ REF_LIB_OBJS := $(patsubst $(REF)/libs/%.cpp,$(REFDRV)/obj/%.o,$(REF_LIB_SRCS))
 SHIM_OBJS    := $(REFDRV)/obj/shim/occa_spn.o $(REFDRV)/obj/shim/mpi_shim.o $(REFDRV)/obj/shim/minilapack.o
 
 ref-drivers:
-	@if [ -d $(REF)/BS ]; then $(MAKE) --no-print-directory $(foreach n,0 1 2 3 4 5 6 7 8,$(REFDRV)/BS$(n)); \
+	@if [ -d $(REF)/BS ]; then $(MAKE) --no-print-directory $(foreach n,0 1 2 3 4 5 6 7 8,$(REFDRV)/BS$(n)) $(REFDRV)/ogs_check; \
 	 else echo "ref-drivers: $(REF) absent, keeping prebuilt $(REFDRV) (if any)"; fi
 
 $(REFDRV)/obj/%.o: $(REF)/libs/%.cpp include/shim/occa.hpp include/shim/mpi.h
@@ -87,6 +87,10 @@ $(REFDRV)/obj/shim/%.o: $(SHIM)/%.cpp include/shim/occa.hpp include/shim/mpi.h i
 	$(CXX) $(REF_CXXFLAGS) -c -o $@ $<
 $(REFDRV)/libref_host_layer.a: $(REF_LIB_OBJS)
 	ar rcs $@ $^
+
+# the reference's ogs_t on the device against its own host path (tests/cpp/ref_ogs_device_check.cpp)
+$(REFDRV)/ogs_check: tests/cpp/ref_ogs_device_check.cpp $(REFDRV)/libref_host_layer.a $(SHIM_OBJS) $(LIBDIR)/libspn_b200.so
+	$(CXX) $(REF_CXXFLAGS) -fPIE -o $@ $< $(SHIM_OBJS) $(REFDRV)/libref_host_layer.a -L$(LIBDIR) -lspn_b200 -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)'
 
 define REF_BS
 $(REFDRV)/BS$(1): $(REF)/BS/BS$(1)/bs$(1)Main.cpp $(wildcard $(REF)/BS/BS$(1)/src/*.cpp) $(REFDRV)/libref_host_layer.a $(SHIM_OBJS) $(LIBDIR)/libspn_b200.so

@@ -96,3 +96,42 @@ def test_every_reference_driver_runs_on_the_b200():
         s = run([need(os.path.join(SERIAL, f"BS{n}")), "-m", "Serial"] + args)
         ms = re.search(rf"BS{n} = \[(\d+), (\d+),", s.stdout)
         assert ms and ms.group(2) == m.group(2)
+
+
+SPNRUN = os.path.join(ROOT, "streamparanumal_b200", "bin", "spnrun")
+CHECK_LINE = r"ogs_check: P=(\d+) N=(\d+) Nlocal=(\d+) Ngather=(\d+) gatherScatter=(\d+) gather=(\d+) scatter=(\d+)"
+
+
+def _ogs_check(exe, ranks, mesh_args, mode=()):
+    cmd = ([SPNRUN, "-np", str(ranks)] if ranks > 1 else []) + [exe] + list(mode) + list(mesh_args)
+    r = run(cmd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(CHECK_LINE, r.stdout)
+    assert m, r.stdout + r.stderr
+    assert int(m.group(1)) == ranks
+    assert (int(m.group(5)), int(m.group(6)), int(m.group(7))) == (0, 0, 0), r.stdout
+    return int(m.group(4))
+
+
+@pytest.mark.parametrize("ranks", [1, 2, 4])
+def test_ogs_check_is_sound_on_the_reference_serial_backend(ranks):
+    """tests/cpp/ref_ogs_device_check.cpp on the HOST backend: the reference's deviceMemory path (its own OKL kernels compiled
+    for the CPU) against its host-memory path — validates the check that the GPU test below relies on"""
+    ng = _ogs_check(need(os.path.join(SERIAL, "ogs_check")), ranks, ["-nx", "3", "-ny", "3", "-nz", "2", "-p", "4"], mode=["-m", "Serial"])
+    # global nodes of the mesh: the process grid multiplies the per-rank box (libs/mesh/meshSetupBoxHex3D.cpp)
+    grid = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1)}[ranks]
+    assert ng == (3 * grid[0] * 4 + 1) * (3 * grid[1] * 4 + 1) * (2 * grid[2] * 4 + 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [1, 2, 4])
+def test_reference_ogs_device_path_equals_its_host_path_on_the_b200(ranks):
+    """the reference's mesh_t + ogs_t, unchanged, on the sm_100a backend: GatherScatter / Gather / Scatter on device memory
+    (ogsOperator_t -> kernel_t -> C ABI; at P > 1 the reference's own pairwise exchange over the MPI stand-in, one GPU per
+    rank) equal the reference's host-memory overloads bit for bit"""
+    import torch
+    if torch.cuda.device_count() < ranks:
+        pytest.skip(f"needs {ranks} GPUs, box has {torch.cuda.device_count()}")
+    exe = need(os.path.join(DRV, "ogs_check"))
+    _ogs_check(exe, ranks, ["-nx", "6", "-ny", "5", "-nz", "4", "-p", "7"])
+    _ogs_check(exe, ranks, ["-nx", "3", "-ny", "2", "-nz", "2", "-p", "1"])
