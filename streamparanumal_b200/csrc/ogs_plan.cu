@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <atomic>
 #include <new>
+#include <thread>
+#include <system_error>
 #include <vector>
 #include "ogs_tile.cuh"
 
@@ -172,6 +174,46 @@ int dispatch_type(const spn_ogs_plan* p, int K, const void* in, void* out, int t
 
 }  // namespace
 
+// rows [r0, r1) packed greedily into tiles of whole consecutive rows with at most 32 non-zeros; empty rows and rows
+// longer than a tile go to the irregular list
+constexpr int kPackChunkRows = 1 << 20;
+struct PackOut {
+  std::vector<OgsTileDesc> tiles;
+  std::vector<int> irr;
+  int bad = 0;  // SPN_ERR_* when the row starts are not monotone / memory ran out
+};
+static void pack_rows(const int* rowStarts, int r0, int r1, PackOut& out) {
+  try {
+    out.tiles.reserve((size_t)((long long)rowStarts[r1] - rowStarts[r0]) / 24 + 16);
+    OgsTileDesc cur;
+    int cur_n = 0;
+    auto flush = [&]() {
+      if (cur_n > 0) out.tiles.push_back(cur);
+      cur_n = 0;
+    };
+    for (int r = r0; r < r1; ++r) {
+      const int s = rowStarts[r], len = rowStarts[r + 1] - s;
+      if (len < 0) { out.bad = SPN_ERR_INVALID_ARGUMENT; return; }
+      if (len == 0 || len > 32) {
+        flush();
+        out.irr.push_back(r);
+        continue;
+      }
+      if (cur_n + len > 32) flush();
+      if (cur_n == 0) {
+        cur.start = s;
+        cur.row0 = r;
+        cur.last = 0u;
+      }
+      cur_n += len;
+      cur.last |= 1u << (cur_n - 1);
+    }
+    flush();
+  } catch (const std::bad_alloc&) {
+    out.bad = SPN_ERR_OUT_OF_MEMORY;
+  }
+}
+
 extern "C" {
 
 static int status_of_cuda(int rc) { return rc == (int)cudaErrorMemoryAllocation ? SPN_ERR_OUT_OF_MEMORY : rc; }
@@ -229,36 +271,40 @@ int spn_ogs_plan_create(spn_ogs_plan_t* plan, int Nrows, int Ncols, const int* h
   p->Ncols = Ncols;
   (void)h_colIds;  // reserved for layouts that need the host copy of the ids (none in use: profiles/r01_notes.md)
 
-  // greedy packing of whole consecutive rows into <=32-nnz tiles
+  // greedy packing of whole consecutive rows into <=32-nnz tiles, by chunks of kPackChunkRows rows on host threads
+  // (a tile never spans a chunk boundary: at most one tile more per 2^20 rows than one serial sweep, and the tiling does
+  // not depend on the thread count)
   std::vector<OgsTileDesc> tiles;
   std::vector<int> irr;
   try {
-    tiles.reserve((size_t)(p->nnz / 24) + 16);
-    OgsTileDesc cur;
-    int cur_n = 0;
-    auto flush = [&]() {
-      if (cur_n > 0) tiles.push_back(cur);
-      cur_n = 0;
+    const int nchunks = (Nrows + kPackChunkRows - 1) / kPackChunkRows;
+    std::vector<PackOut> parts((size_t)nchunks);
+    std::atomic<int> next{0};
+    auto worker = [&]() {
+      for (int c = next.fetch_add(1); c < nchunks; c = next.fetch_add(1))
+        pack_rows(h_rowStarts, c * kPackChunkRows, std::min(Nrows, (c + 1) * kPackChunkRows), parts[c]);
     };
-    for (int r = 0; r < Nrows; ++r) {
-      const int s = h_rowStarts[r], len = h_rowStarts[r + 1] - s;
-      if (len < 0) { delete p; return SPN_ERR_INVALID_ARGUMENT; }
-      if (len == 0 || len > 32) {
-        flush();
-        irr.push_back(r);
-        continue;
-      }
-      if (cur_n + len > 32) flush();
-      if (cur_n == 0) {
-        cur.start = s;
-        cur.row0 = r;
-        cur.last = 0u;
-      }
-      cur_n += len;
-      cur.last |= 1u << (cur_n - 1);
+    const int nthreads = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, nchunks}));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+    worker();
+    for (std::thread& t : pool) t.join();
+    size_t nt = 0, ni = 0;
+    for (const PackOut& o : parts) {
+      if (o.bad) { delete p; return o.bad; }
+      nt += o.tiles.size();
+      ni += o.irr.size();
     }
-    flush();
+    tiles.reserve(nt);
+    irr.reserve(ni);
+    for (const PackOut& o : parts) {
+      tiles.insert(tiles.end(), o.tiles.begin(), o.tiles.end());
+      irr.insert(irr.end(), o.irr.begin(), o.irr.end());
+    }
   } catch (const std::bad_alloc&) {
+    delete p;
+    return SPN_ERR_OUT_OF_MEMORY;
+  } catch (const std::system_error&) {  // no thread could be started
     delete p;
     return SPN_ERR_OUT_OF_MEMORY;
   }

@@ -136,38 +136,40 @@ int spn_host_ogs_array(spn_host_ogs_t h, int which, int mode, const int** ptr, l
   const ogs::ogs_t& o = h->ogs;
   if (!o.gatherLocal || !o.gatherHalo) return SPN_ERR_INVALID_ARGUMENT;
   const ogs::ogsExchangeData_t& d = o.data[mode];
-  const std::vector<int>* v = nullptr;
+  const int* data = nullptr;
+  size_t count = 0;
+  auto set = [&](const auto& vec) { data = vec.data(); count = vec.size(); };
   // an Unsigned operator aliases N to T (libs/ogs/ogsOperator.cpp:644-650)
-  auto nOrT = [](const ogs::ogsOperator_t& op, bool starts) -> const std::vector<int>* {
-    if (op.kind == ogs::Signed) return starts ? &op.rowStartsN : &op.colIdsN;
-    return starts ? &op.rowStartsT : &op.colIdsT;
+  auto nOrT = [&](const ogs::ogsOperator_t& op, bool starts) {
+    if (op.kind == ogs::Signed) set(starts ? op.rowStartsN : op.colIdsN);
+    else set(starts ? op.rowStartsT : op.colIdsT);
   };
   switch (which) {
-    case 0: v = &o.gatherLocal->rowStartsT; break;
-    case 1: v = &o.gatherLocal->colIdsT; break;
-    case 2: v = nOrT(*o.gatherLocal, true); break;
-    case 3: v = nOrT(*o.gatherLocal, false); break;
-    case 4: v = &o.gatherHalo->rowStartsT; break;
-    case 5: v = &o.gatherHalo->colIdsT; break;
-    case 6: v = nOrT(*o.gatherHalo, true); break;
-    case 7: v = nOrT(*o.gatherHalo, false); break;
-    case 8: v = &d.sendIds; break;
-    case 9: v = &d.sendRanks; break;
-    case 10: v = &d.sendCounts; break;
-    case 11: v = &d.sendOffsets; break;
-    case 12: v = &d.recvRanks; break;
-    case 13: v = &d.recvCounts; break;
-    case 14: v = &d.recvOffsets; break;
-    case 15: v = &d.cmbStarts; break;
-    case 16: v = &d.cmbIds; break;
-    case 17: v = &d.recvRows; break;
-    case 18: v = &d.rowSendStarts; break;
-    case 19: v = &d.rowSendDst; break;
-    case 20: v = &d.slotDst; break;
+    case 0: set(o.gatherLocal->rowStartsT); break;
+    case 1: set(o.gatherLocal->colIdsT); break;
+    case 2: nOrT(*o.gatherLocal, true); break;
+    case 3: nOrT(*o.gatherLocal, false); break;
+    case 4: set(o.gatherHalo->rowStartsT); break;
+    case 5: set(o.gatherHalo->colIdsT); break;
+    case 6: nOrT(*o.gatherHalo, true); break;
+    case 7: nOrT(*o.gatherHalo, false); break;
+    case 8: set(d.sendIds); break;
+    case 9: set(d.sendRanks); break;
+    case 10: set(d.sendCounts); break;
+    case 11: set(d.sendOffsets); break;
+    case 12: set(d.recvRanks); break;
+    case 13: set(d.recvCounts); break;
+    case 14: set(d.recvOffsets); break;
+    case 15: set(d.cmbStarts); break;
+    case 16: set(d.cmbIds); break;
+    case 17: set(d.recvRows); break;
+    case 18: set(d.rowSendStarts); break;
+    case 19: set(d.rowSendDst); break;
+    case 20: set(d.slotDst); break;
     default: return SPN_ERR_INVALID_ARGUMENT;
   }
-  *ptr = v->data();
-  *len = (long long)v->size();
+  *ptr = data;
+  *len = (long long)count;
   return SPN_SUCCESS;
 }
 int spn_host_ogs_halo_labels(spn_host_ogs_t h, const long long** ptr, long long* len) {

@@ -64,9 +64,9 @@ class ogsOperator_t {
  public:
   Kind kind = Unsigned;
   dlong Ncols = 0, NrowsN = 0, NrowsT = 0, nnzN = 0, nnzT = 0;
-  std::vector<dlong> rowStartsT, colIdsT;  // NrowsT+1, nnzT
-  std::vector<dlong> rowStartsN, colIdsN;  // NrowsT+1 (rows >= NrowsN are empty), nnzN
-  std::vector<hlong> rowLabel;             // |label| of every row
+  hvec<dlong> rowStartsT, colIdsT;  // NrowsT+1, nnzT
+  hvec<dlong> rowStartsN, colIdsN;  // NrowsT+1 (rows >= NrowsN are empty), nnzN
+  hvec<hlong> rowLabel;             // |label| of every row
 
   // device side
   deviceMemory<dlong> o_rowStartsT, o_colIdsT, o_rowStartsN, o_colIdsN, o_blockRowStartsT, o_blockRowStartsN;

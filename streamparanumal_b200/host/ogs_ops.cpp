@@ -52,7 +52,7 @@ void ogsOperator_t::upload(platform_t& platform, bool tile_plans) {
   }
   // launch partitions of the CSR kernels: whole rows, <= spn_ogs_nodes_per_block() non-zeros per block
   // (the role of blockRows(), libs/ogs/ogsOperator.cpp:522-594; a longer single row gets its own block)
-  auto partition = [&](const std::vector<dlong>& rs, dlong nrows, dlong& nblocks) {
+  auto partition = [&](const hvec<dlong>& rs, dlong nrows, dlong& nblocks) {
     const dlong limit = spn_ogs_nodes_per_block();
     std::vector<dlong> blocks(1, 0);
     dlong r = 0;

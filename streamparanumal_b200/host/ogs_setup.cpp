@@ -53,6 +53,17 @@ struct RefLcg {
     x = 6364136223846793005ULL * x + 1ULL;
     return v < 0 ? (v == INT_MIN ? v : -v) : v;  // std::abs(int), INT_MIN left as the reference leaves it
   }
+  // advance by k draws in O(log k): the k-fold composition of x -> a x + c by repeated squaring, so that a thread can
+  // start at the draw of its first label group
+  void skip(unsigned long long k) {
+    unsigned long long curA = 6364136223846793005ULL, curC = 1ULL, accA = 1ULL, accC = 0ULL;
+    for (; k; k >>= 1) {
+      if (k & 1) { accC = accC * curA + curC; accA *= curA; }
+      curC = (curA + 1ULL) * curC;
+      curA *= curA;
+    }
+    x = accA * x + accC;
+  }
 };
 
 // 0: members of a label group in (source rank, source order) — the stable order, the default;
@@ -78,7 +89,7 @@ struct Key {
 // Stable parallel LSD radix sort of keys[i] = {label, i} by label (11-bit digits, as many passes as the largest label
 // needs).  Stable + the initial order i ascending means equal labels stay in ascending position: the (label, idx) order
 // the grouping below relies on.  Replaces a comparison sort of 2^27 16-byte keys (3-5 s of the setup) by 3 streaming passes.
-void sort_keys_by_label(std::vector<Key>& keys) {
+void sort_keys_by_label(hvec<Key>& keys) {
   const size_t n = keys.size();
   if (n < 2) return;
   hlong maxLabel = 0;
@@ -87,7 +98,7 @@ void sort_keys_by_label(std::vector<Key>& keys) {
   constexpr int BITS = 11, BUCKETS = 1 << BITS;
   int passes = 1;
   while (passes * BITS < 63 && (maxLabel >> (passes * BITS)) != 0) ++passes;
-  std::vector<Key> tmp(n);
+  hvec<Key> tmp(n);
   Key* src = keys.data();
   Key* dst = tmp.data();
   const int T = omp_get_max_threads();
@@ -144,25 +155,59 @@ T exclusive_scan(T* v, size_t n) {
   return part[P];
 }
 
+// Work split of [0, n) into `chunks` contiguous pieces, one per loop iteration of a static OpenMP loop: the order-
+// preserving selections below count per chunk, prefix-sum the counts, and write each chunk at its offset.
+inline dlong chunk_lo(dlong n, int c, int chunks) { return (dlong)((long long)n * c / chunks); }
+
+// offsets[c] = number of i in the chunks before c with keep(i); offsets[chunks] = total
+template <class Keep>
+std::vector<dlong> count_selected(dlong n, int chunks, Keep keep) {
+  std::vector<dlong> offsets((size_t)chunks + 1, 0);
+#pragma omp parallel for schedule(static, 1)
+  for (int c = 0; c < chunks; ++c) {
+    dlong cnt = 0;
+    for (dlong i = chunk_lo(n, c, chunks), e = chunk_lo(n, c + 1, chunks); i < e; ++i) cnt += keep(i) ? 1 : 0;
+    offsets[c + 1] = cnt;
+  }
+  for (int c = 0; c < chunks; ++c) offsets[c + 1] += offsets[c];
+  return offsets;
+}
+
+// emit(i, position) for every selected i, positions ascending with i
+template <class Keep, class Emit>
+void emit_selected(dlong n, int chunks, const std::vector<dlong>& offsets, Keep keep, Emit emit) {
+#pragma omp parallel for schedule(static, 1)
+  for (int c = 0; c < chunks; ++c) {
+    dlong o = offsets[c];
+    for (dlong i = chunk_lo(n, c, chunks), e = chunk_lo(n, c + 1, chunks); i < e; ++i)
+      if (keep(i)) emit(i, o++);
+  }
+}
+
+template <typename T>
+void parallel_fill(T* v, size_t n, T value) {
+#pragma omp parallel for
+  for (size_t i = 0; i < n; ++i) v[i] = value;
+}
+
 // Number the label groups of one entry set and build both CSR variants.
 // entries: signed labels `ids` at columns `cols` (cols strictly ascending).
 // Rows = label groups in first-appearance order, groups with a positive copy first (libs/ogs/ogsSetup.cpp:492-559);
 // columns ascend inside a row (stable SortByRow, :561-579).  Every pass is a parallel loop or a prefix sum.
-std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const std::vector<hlong>& ids,
-                                              const std::vector<dlong>& cols) {
+std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const hvec<hlong>& ids, const hvec<dlong>& cols) {
   auto op = std::make_shared<ogsOperator_t>();
   op->kind = (kind == Unsigned) ? Unsigned : Signed;
   op->Ncols = Ncols;
   const dlong n = (dlong)ids.size();
   op->nnzT = n;
 
-  std::vector<Key> keys((size_t)n);
+  hvec<Key> keys((size_t)n);
 #pragma omp parallel for
   for (dlong i = 0; i < n; ++i) keys[i] = Key{habs(ids[i]), i};
   sort_keys_by_label(keys);  // groups contiguous, members in ascending entry (= column) order
 
   // group starts in sorted order
-  std::vector<dlong> groupOfSorted((size_t)n);  // first: 1 at a group start, then the group index
+  hvec<dlong> groupOfSorted((size_t)n);  // first: 1 at a group start, then the group index
 #pragma omp parallel for
   for (dlong i = 0; i < n; ++i) groupOfSorted[i] = (i == 0 || keys[i].label != keys[i - 1].label) ? 1 : 0;
   const dlong NT = n ? exclusive_scan(groupOfSorted.data(), (size_t)n) : 0;  // groupOfSorted[i] = groups before i ...
@@ -171,12 +216,12 @@ std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const std:
     if (i == 0 || keys[i].label != keys[i - 1].label) groupOfSorted[i] += 1;
 #pragma omp parallel for
   for (dlong i = 0; i < n; ++i) groupOfSorted[i] -= 1;
-  std::vector<dlong> groupStart((size_t)NT + 1);  // sorted position of the first member
+  hvec<dlong> groupStart((size_t)NT + 1);  // sorted position of the first member
 #pragma omp parallel for
   for (dlong i = 0; i < n; ++i)
     if (i == 0 || groupOfSorted[i] != groupOfSorted[i - 1]) groupStart[groupOfSorted[i]] = i;
   groupStart[NT] = n;
-  std::vector<char> groupPos((size_t)NT, 0);  // has a positive copy on this rank
+  hvec<char> groupPos((size_t)NT);  // has a positive copy on this rank
 #pragma omp parallel for
   for (dlong g = 0; g < NT; ++g) {
     char pos = 0;
@@ -184,7 +229,9 @@ std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const std:
     groupPos[g] = pos;
   }
   // first-appearance order, positive groups first: flags in ENTRY order at each group's first member, two prefix sums
-  std::vector<dlong> headP((size_t)n, 0), headM((size_t)n, 0);
+  hvec<dlong> headP((size_t)n), headM((size_t)n);
+  parallel_fill(headP.data(), (size_t)n, (dlong)0);
+  parallel_fill(headM.data(), (size_t)n, (dlong)0);
 #pragma omp parallel for
   for (dlong g = 0; g < NT; ++g) {
     const dlong first = keys[groupStart[g]].idx;  // smallest entry index of the group
@@ -192,7 +239,7 @@ std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const std:
   }
   const dlong NP = n ? exclusive_scan(headP.data(), (size_t)n) : 0;
   if (n) exclusive_scan(headM.data(), (size_t)n);
-  std::vector<dlong> rowOfGroup((size_t)NT);
+  hvec<dlong> rowOfGroup((size_t)NT);
 #pragma omp parallel for
   for (dlong g = 0; g < NT; ++g) {
     const dlong first = keys[groupStart[g]].idx;
@@ -204,8 +251,9 @@ std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const std:
   op->NrowsN = NP;
 
   // CSR "T": every copy.  Row lengths = group sizes; members of a group are already in ascending column order.
-  op->rowLabel.assign((size_t)NT, 0);
-  op->rowStartsT.assign((size_t)NT + 1, 0);
+  op->rowLabel.resize((size_t)NT);
+  op->rowStartsT.resize((size_t)NT + 1);
+  op->rowStartsT[NT] = 0;
 #pragma omp parallel for
   for (dlong g = 0; g < NT; ++g) {
     const dlong row = rowOfGroup[g];
@@ -222,7 +270,8 @@ std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const std:
   // CSR "N": positive copies only (libs/ogs/ogsOperator.cpp:620-643).  rowStartsN carries NrowsT+1
   // entries (rows >= NrowsN are empty) so kernels may walk the T row partition over it.
   if (op->kind == Signed) {
-    op->rowStartsN.assign((size_t)NT + 1, 0);
+    op->rowStartsN.resize((size_t)NT + 1);
+    op->rowStartsN[NT] = 0;
 #pragma omp parallel for
     for (dlong g = 0; g < NT; ++g) {
       dlong c = 0;
@@ -503,42 +552,61 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   // shared between ranks act — the reference builds no gatherLocal for it (ogsSetup.cpp:592-603)
   halo_only = (kind == Halo);
 
+  const int chunks = std::max(1, omp_get_max_threads()) * 4;  // pieces of the order-preserving parallel passes
+
   // ---- non-zero labels, in column order ----------------------------------------------------
-  dlong Nids = 0;
-  for (dlong n = 0; n < N; ++n) Nids += (ids[n] != 0) ? 1 : 0;
-  std::vector<dlong> colIds((size_t)Nids);
-  std::vector<hlong> baseIds((size_t)Nids);
-  {
-    dlong c = 0;
-    for (dlong n = 0; n < N; ++n)
-      if (ids[n] != 0) { colIds[c] = n; baseIds[c] = ids[n]; ++c; }
-  }
+  auto nonzero = [&](dlong n) { return ids[n] != 0; };
+  const std::vector<dlong> nzOffsets = count_selected(N, chunks, nonzero);
+  const dlong Nids = nzOffsets[chunks];
+  hvec<dlong> colIds((size_t)Nids);
+  hvec<hlong> baseIds((size_t)Nids);
+  emit_selected(N, chunks, nzOffsets, nonzero, [&](dlong n, dlong c) { colIds[c] = n; baseIds[c] = ids[n]; });
 
   phase.lap("non-zero labels");
   // ---- 1. directory round ------------------------------------------------------------------
+  // label L lives on directory rank |L| % size; the send buffer is ordered by destination, entries of one destination
+  // in column order (per-chunk histograms, destination-major / chunk-minor offsets)
   std::vector<int> sendCounts(size, 0), sendOffsets(size + 1, 0), recvCounts(size, 0), recvOffsets(size + 1, 0);
-  for (dlong n = 0; n < Nids; ++n) sendCounts[habs(baseIds[n]) % size]++;
-  for (int r = 0; r < size; ++r) sendOffsets[r + 1] = sendOffsets[r] + sendCounts[r];
-  std::vector<dlong> sendPos((size_t)Nids);  // entry n sits at slot sendPos[n] of the send buffer (stable by dest)
-  std::vector<hlong> sendLabels((size_t)Nids);
+  hvec<dlong> sendPos((size_t)Nids);  // entry n sits at slot sendPos[n] of the send buffer (stable by dest)
+  hvec<hlong> sendLabels((size_t)Nids);
   {
-    std::vector<int> fill(sendOffsets.begin(), sendOffsets.end() - 1);
-    for (dlong n = 0; n < Nids; ++n) {
-      const int dst = (int)(habs(baseIds[n]) % size);
-      sendPos[n] = fill[dst]++;
-      sendLabels[sendPos[n]] = baseIds[n];
+    std::vector<dlong> hist((size_t)chunks * size, 0);
+#pragma omp parallel for schedule(static, 1)
+    for (int c = 0; c < chunks; ++c) {
+      dlong* h = hist.data() + (size_t)c * size;
+      for (dlong n = chunk_lo(Nids, c, chunks), e = chunk_lo(Nids, c + 1, chunks); n < e; ++n) h[habs(baseIds[n]) % size]++;
+    }
+    dlong run = 0;
+    for (int r = 0; r < size; ++r) {
+      sendOffsets[r] = (int)run;
+      for (int c = 0; c < chunks; ++c) {
+        const dlong cnt = hist[(size_t)c * size + r];
+        hist[(size_t)c * size + r] = run;
+        run += cnt;
+      }
+      sendCounts[r] = (int)run - sendOffsets[r];
+    }
+    sendOffsets[size] = (int)run;
+#pragma omp parallel for schedule(static, 1)
+    for (int c = 0; c < chunks; ++c) {
+      dlong* h = hist.data() + (size_t)c * size;
+      for (dlong n = chunk_lo(Nids, c, chunks), e = chunk_lo(Nids, c + 1, chunks); n < e; ++n) {
+        const dlong pos = h[habs(baseIds[n]) % size]++;
+        sendPos[n] = pos;
+        sendLabels[pos] = baseIds[n];
+      }
     }
   }
   comm.Alltoall(sendCounts.data(), recvCounts.data());
   for (int r = 0; r < size; ++r) recvOffsets[r + 1] = recvOffsets[r] + recvCounts[r];
   const dlong recvN = recvOffsets[size];
-  std::vector<hlong> recvLabels((size_t)recvN);
+  hvec<hlong> recvLabels((size_t)recvN);
   comm.Alltoallv(sendLabels.data(), sendCounts.data(), sendOffsets.data(), recvLabels.data(), recvCounts.data(),
                  recvOffsets.data());
 
   phase.lap("route labels to directory ranks");
   // group the received copies by |label|; inside a group they stay in (source rank, source order)
-  std::vector<Key> keys((size_t)recvN);
+  hvec<Key> keys((size_t)recvN);
 #pragma omp parallel for
   for (dlong i = 0; i < recvN; ++i) keys[i] = Key{habs(recvLabels[i]), i};
   sort_keys_by_label(keys);
@@ -549,7 +617,6 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
 
   // positive-copy pick of the reference (libs/ogs/ogsSetup.cpp:355-382): group n of this directory rank, in ascending
   // label order, takes member  rands[n] % (group size)  with rands from the rank-seeded LCG
-  RefLcg lcg((unsigned long long)rank);
   std::vector<std::pair<hlong, dlong>> refOrder;  // pick mode 1: (|label|, receive slot) as std::sort leaves them
   if (unique && pick_mode() == 1) {
     refOrder.resize((size_t)recvN);
@@ -558,52 +625,80 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
               [](const std::pair<hlong, dlong>& a, const std::pair<hlong, dlong>& b) { return a.first < b.first; });
   }
 
-  std::vector<int> recvShared((size_t)recvN, 0);
-  std::vector<std::vector<hlong>> reply(size);  // per source rank: [label, nranks, (rank*2+positive)...] per shared label
+  // label groups = runs of equal |label| in the sorted keys
+  auto opens_group = [&](dlong i) { return i == 0 || keys[i].label != keys[i - 1].label; };
+  const std::vector<dlong> groupOffsets = count_selected(recvN, chunks, opens_group);
+  const dlong Ngroups = groupOffsets[chunks];
+  hvec<dlong> groupStart((size_t)Ngroups + 1);
+  emit_selected(recvN, chunks, groupOffsets, opens_group, [&](dlong i, dlong g) { groupStart[g] = i; });
+  groupStart[Ngroups] = recvN;
+
+  hvec<int> recvShared((size_t)recvN);
+  hvec<char> groupShared((size_t)Ngroups);  // copies on more than one rank
   int is_unique = 1;
-  hlong NsharedLabels = 0;
-  {
-    std::vector<hlong> sharers;
-    for (dlong s = 0; s < recvN;) {
-      dlong e = s + 1;
-      while (e < recvN && keys[e].label == keys[s].label) ++e;
-      const hlong label = keys[s].label;
+  // every group is independent once its draw is known: thread chunks of consecutive groups, the generator skipped
+  // ahead to the chunk's first group (draw n belongs to group n, libs/ogs/ogsSetup.cpp:355-382)
+#pragma omp parallel for schedule(static, 1) reduction(min : is_unique)
+  for (int c = 0; c < chunks; ++c) {
+    const dlong g0 = chunk_lo(Ngroups, c, chunks), g1 = chunk_lo(Ngroups, c + 1, chunks);
+    RefLcg lcg((unsigned long long)rank);
+    if (unique) lcg.skip((unsigned long long)g0);
+    for (dlong g = g0; g < g1; ++g) {
+      const dlong s0 = groupStart[g], e = groupStart[g + 1];
+      const hlong label = keys[s0].label;
       if (unique) {
         // one positive copy per label (libs/ogs/ogsSetup.cpp:364-382)
-        const int m = lcg.next() % (int)(e - s);
-        for (dlong i = s; i < e; ++i) recvLabels[keys[i].idx] = -label;
-        const dlong picked = refOrder.empty() ? keys[s + m].idx : refOrder[(size_t)(s + m)].second;
+        const int m = lcg.next() % (int)(e - s0);
+        for (dlong i = s0; i < e; ++i) recvLabels[keys[i].idx] = -label;
+        const dlong picked = refOrder.empty() ? keys[s0 + m].idx : refOrder[(size_t)(s0 + m)].second;
         recvLabels[picked] = label;
       } else {
         int positives = 0;
-        for (dlong i = s; i < e; ++i) positives += (recvLabels[keys[i].idx] > 0) ? 1 : 0;
+        for (dlong i = s0; i < e; ++i) positives += (recvLabels[keys[i].idx] > 0) ? 1 : 0;
         if (positives != 1) is_unique = 0;
       }
-      const int r0 = rank_of(keys[s].idx), r1 = rank_of(keys[e - 1].idx);
-      if (r0 != r1) {
-        ++NsharedLabels;
-        sharers.clear();
-        for (dlong i = s; i < e;) {
-          const int r = rank_of(keys[i].idx);
-          int pos = 0;
-          dlong j = i;
-          for (; j < e && rank_of(keys[j].idx) == r; ++j) pos |= (recvLabels[keys[j].idx] > 0) ? 1 : 0;
-          sharers.push_back((hlong)r * 2 + pos);
-          i = j;
-        }
-        for (hlong sp : sharers) {
-          std::vector<hlong>& out = reply[(int)(sp >> 1)];
-          out.push_back(label);
-          out.push_back((hlong)sharers.size());
-          out.insert(out.end(), sharers.begin(), sharers.end());
-        }
-        for (dlong i = s; i < e; ++i) recvShared[keys[i].idx] = 1;
+      // members are in ascending receive slot = ascending source rank: first and last differ iff the label is shared
+      const int shared = (size > 1 && rank_of(keys[s0].idx) != rank_of(keys[e - 1].idx)) ? 1 : 0;
+      groupShared[g] = (char)shared;
+      for (dlong i = s0; i < e; ++i) recvShared[keys[i].idx] = shared;
+    }
+  }
+
+  // replies for the shared labels only (the surface of the partition), in ascending label order
+  std::vector<std::vector<hlong>> reply(size);  // per source rank: [label, nranks, (rank*2+positive)...] per shared label
+  hlong NsharedLabels = 0;
+  {
+    auto is_shared = [&](dlong g) { return groupShared[g] != 0; };
+    const std::vector<dlong> sharedOffsets = count_selected(Ngroups, chunks, is_shared);
+    NsharedLabels = sharedOffsets[chunks];
+    hvec<dlong> sharedGroups((size_t)NsharedLabels);
+    emit_selected(Ngroups, chunks, sharedOffsets, is_shared, [&](dlong g, dlong q) { sharedGroups[q] = g; });
+    std::vector<hlong> sharers;
+    for (dlong q = 0; q < (dlong)NsharedLabels; ++q) {
+      const dlong g = sharedGroups[q];
+      const dlong s0 = groupStart[g], e = groupStart[g + 1];
+      const hlong label = keys[s0].label;
+      sharers.clear();
+      for (dlong i = s0; i < e;) {
+        const int r = rank_of(keys[i].idx);
+        int pos = 0;
+        dlong j = i;
+        for (; j < e && rank_of(keys[j].idx) == r; ++j) pos |= (recvLabels[keys[j].idx] > 0) ? 1 : 0;
+        sharers.push_back((hlong)r * 2 + pos);
+        i = j;
       }
-      s = e;
+      for (hlong sp : sharers) {
+        std::vector<hlong>& out = reply[(int)(sp >> 1)];
+        out.push_back(label);
+        out.push_back((hlong)sharers.size());
+        out.insert(out.end(), sharers.begin(), sharers.end());
+      }
     }
   }
   keys.clear();
   keys.shrink_to_fit();
+  groupStart.clear();
+  groupStart.shrink_to_fit();
 
   phase.lap("groups: shared / pick");
   comm.Allreduce(is_unique, Comm::Min);
@@ -617,12 +712,13 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   }
 
   // answers back to the sources
-  std::vector<int> sharedOfSlot((size_t)Nids);
+  hvec<int> sharedOfSlot((size_t)Nids);
   comm.Alltoallv(recvShared.data(), recvCounts.data(), recvOffsets.data(), sharedOfSlot.data(), sendCounts.data(),
                  sendOffsets.data());
   if (unique) {
     comm.Alltoallv(recvLabels.data(), recvCounts.data(), recvOffsets.data(), sendLabels.data(), sendCounts.data(),
                    sendOffsets.data());
+#pragma omp parallel for
     for (dlong n = 0; n < Nids; ++n) {
       baseIds[n] = sendLabels[sendPos[n]];
       ids[colIds[n]] = baseIds[n];  // write the signs back (libs/ogs/ogsSetup.cpp:147-150)
@@ -651,12 +747,26 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
 
   phase.lap("answers back to the sources");
   // ---- 2. split into local / halo entries and number the rows ---------------------------------
-  std::vector<hlong> localIds, haloIds;
-  std::vector<dlong> localCols, haloCols;
-  for (dlong n = 0; n < Nids; ++n) {
-    if (sharedOfSlot[sendPos[n]]) { haloIds.push_back(baseIds[n]); haloCols.push_back(colIds[n]); }
-    else { localIds.push_back(baseIds[n]); localCols.push_back(colIds[n]); }
+  hvec<hlong> localIds, haloIds;
+  hvec<dlong> localCols, haloCols;
+  {
+    auto is_halo = [&](dlong n) { return sharedOfSlot[sendPos[n]] != 0; };
+    auto is_local = [&](dlong n) { return sharedOfSlot[sendPos[n]] == 0; };
+    const std::vector<dlong> haloOffsets = count_selected(Nids, chunks, is_halo);
+    std::vector<dlong> localOffsets((size_t)chunks + 1);
+    for (int c = 0; c <= chunks; ++c) localOffsets[c] = chunk_lo(Nids, c, chunks) - haloOffsets[c];
+    haloIds.resize((size_t)haloOffsets[chunks]);
+    haloCols.resize((size_t)haloOffsets[chunks]);
+    localIds.resize((size_t)localOffsets[chunks]);
+    localCols.resize((size_t)localOffsets[chunks]);
+    emit_selected(Nids, chunks, haloOffsets, is_halo, [&](dlong n, dlong q) { haloIds[q] = baseIds[n]; haloCols[q] = colIds[n]; });
+    emit_selected(Nids, chunks, localOffsets, is_local, [&](dlong n, dlong q) { localIds[q] = baseIds[n]; localCols[q] = colIds[n]; });
   }
+  sendPos.clear(); sendPos.shrink_to_fit();
+  sendLabels.clear(); sendLabels.shrink_to_fit();
+  sharedOfSlot.clear(); sharedOfSlot.shrink_to_fit();
+  baseIds.clear(); baseIds.shrink_to_fit();
+  colIds.clear(); colIds.shrink_to_fit();
   phase.lap("split local / halo");
   gatherLocal = build_operator(kind, N, localIds, localCols);
   phase.lap("local operator");

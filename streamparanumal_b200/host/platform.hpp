@@ -12,6 +12,7 @@
 #include <chrono>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "comm.hpp"
@@ -25,6 +26,25 @@ using hlong = long long int;
 class platform_t;
 class kernel_t;
 class properties_t;
+
+// std::vector whose resize / sized constructor leaves trivially-constructible elements uninitialised: the big index
+// arrays of the ogs setup are written in full by parallel loops right after they are sized, and the serial value-
+// initialisation of std::vector (one thread first-touching every page, 0.5 s per GB) was a third of the setup time.
+template <typename T>
+struct NoInitAlloc : std::allocator<T> {
+  template <typename U>
+  struct rebind { using other = NoInitAlloc<U>; };
+  NoInitAlloc() = default;
+  template <typename U>
+  NoInitAlloc(const NoInitAlloc<U>&) {}
+  template <typename U, typename... Args>
+  void construct(U* p, Args&&... args) {
+    if constexpr (sizeof...(Args) == 0) ::new ((void*)p) U;
+    else ::new ((void*)p) U(std::forward<Args>(args)...);
+  }
+};
+template <typename T>
+using hvec = std::vector<T, NoInitAlloc<T>>;
 
 namespace detail {
 struct DeviceBlock {
@@ -141,8 +161,8 @@ class platform_t {
     m.copyFrom(src, (std::ptrdiff_t)count);
     return m;
   }
-  template <typename T>
-  deviceMemory<T> malloc(const std::vector<T>& src) { return malloc<T>(src.size(), src.data()); }
+  template <typename T, typename A>
+  deviceMemory<T> malloc(const std::vector<T, A>& src) { return malloc<T>(src.size(), src.data()); }
   template <typename T>
   pinnedMemory<T> hostMalloc(size_t count) {
     auto blk = std::make_shared<detail::DeviceBlock>();

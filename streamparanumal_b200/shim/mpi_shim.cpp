@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <execinfo.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -37,6 +38,10 @@ inline int kind_of(MPI_Datatype t) { return (t >> 16) & 0xff; }
 
 [[noreturn]] void fail(const std::string& what) {
   fprintf(stderr, "mpi shim: %s\n", what.c_str());
+  if (getenv("SPN_MPI_BACKTRACE")) {
+    void* frames[48];
+    backtrace_symbols_fd(frames, backtrace(frames, 48), 2);
+  }
   abort();
 }
 
@@ -93,7 +98,9 @@ Comm& comm_of(MPI_Comm c) {
 void deliver(Message&& m) {
   for (auto it = g_posted.begin(); it != g_posted.end(); ++it) {
     if (it->comm == m.comm && (it->tag == m.tag || it->tag == MPI_ANY_TAG) && (it->src == m.src || it->src == MPI_ANY_SOURCE)) {
-      if (m.data.size() > it->bytes) fail("message longer than the posted receive");
+      if (m.data.size() > it->bytes)
+        fail("message longer than the posted receive (comm " + std::to_string(m.comm) + ", source " + std::to_string(m.src) + ", tag " +
+             std::to_string(m.tag) + ": " + std::to_string(m.data.size()) + " bytes sent, " + std::to_string(it->bytes) + " posted)");
       if (!m.data.empty()) memcpy(it->buf, m.data.data(), m.data.size());
       g_done[it->request] = 1;
       g_posted.erase(it);
@@ -106,7 +113,9 @@ void deliver(Message&& m) {
 bool try_receive(int comm, int src, int tag, void* buf, size_t bytes) {
   for (auto it = g_unexpected.begin(); it != g_unexpected.end(); ++it) {
     if (it->comm == comm && (it->tag == tag || tag == MPI_ANY_TAG) && (it->src == src || src == MPI_ANY_SOURCE)) {
-      if (it->data.size() > bytes) fail("message longer than the receive buffer");
+      if (it->data.size() > bytes)
+        fail("message longer than the receive buffer (comm " + std::to_string(comm) + ", source " + std::to_string(it->src) + ", tag " +
+             std::to_string(it->tag) + ": " + std::to_string(it->data.size()) + " bytes sent, " + std::to_string(bytes) + " posted)");
       if (!it->data.empty()) memcpy(buf, it->data.data(), it->data.size());
       g_unexpected.erase(it);
       return true;
@@ -194,7 +203,9 @@ void send_bytes(int dst, const void* p, size_t n) {
   }
 }
 
+bool g_trace = getenv("SPN_MPI_TRACE") != nullptr;
 void send_message(int comm, int dst_world, int tag, const void* buf, size_t bytes) {
+  if (g_trace) fprintf(stderr, "[%d] send -> %d comm %d tag %d bytes %zu (first int %d)\n", g_rank, dst_world, comm, tag, bytes, bytes >= 4 ? *(const int*)buf : 0);
   if (dst_world == g_rank) {
     Message m{comm, tag, g_rank, std::vector<char>((const char*)buf, (const char*)buf + bytes)};
     deliver(std::move(m));
@@ -435,6 +446,7 @@ int MPI_Isend(const void* buf, int count, MPI_Datatype type, int dest, int tag, 
 int MPI_Irecv(void* buf, int count, MPI_Datatype type, int source, int tag, MPI_Comm c, MPI_Request* request) {
   const int src = source == MPI_ANY_SOURCE ? MPI_ANY_SOURCE : comm_of(c).ranks.at(source);
   const size_t bytes = (size_t)count * bytes_of(type);
+  if (g_trace) fprintf(stderr, "[%d] irecv <- %d comm %d tag %d bytes %zu\n", g_rank, src, c, tag, bytes);
   if (try_receive(c, src, tag, buf, bytes)) {
     *request = new_request(true);
   } else {

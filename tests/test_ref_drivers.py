@@ -99,7 +99,7 @@ def test_every_reference_driver_runs_on_the_b200():
 
 
 SPNRUN = os.path.join(ROOT, "streamparanumal_b200", "bin", "spnrun")
-CHECK_LINE = r"ogs_check: P=(\d+) N=(\d+) Nlocal=(\d+) Ngather=(\d+) gatherScatter=(\d+) gather=(\d+) scatter=(\d+)"
+CHECK_LINE = r"ogs_check: P=(\d+) N=(\d+) Nlocal=(\d+) Ngather=(\d+) gatherScatter=(\d+) gather=(\d+) scatter=(\d+) cases=(\d+)"
 
 
 def _ogs_check(exe, ranks, mesh_args, mode=()):
@@ -110,13 +110,18 @@ def _ogs_check(exe, ranks, mesh_args, mode=()):
     assert m, r.stdout + r.stderr
     assert int(m.group(1)) == ranks
     assert (int(m.group(5)), int(m.group(6)), int(m.group(7))) == (0, 0, 0), r.stdout
+    # GatherScatter(Add): 4 types x 3 modes x K in {1,3} = 24; Gather x3 + Scatter x2 per K, for 2 types = 20
+    assert int(m.group(8)) == 44
     return int(m.group(4))
 
 
 @pytest.mark.parametrize("ranks", [1, 2, 4])
 def test_ogs_check_is_sound_on_the_reference_serial_backend(ranks):
     """tests/cpp/ref_ogs_device_check.cpp on the HOST backend: the reference's deviceMemory path (its own OKL kernels compiled
-    for the CPU) against its host-memory path — validates the check that the GPU test below relies on"""
+    for the CPU) against its host-memory path — validates the check that the GPU test below relies on.
+    (Rank counts are powers of two: the reference's Auto setup builds its crystal router too, and that one breaks at any
+    other count on any MPI — the upper half leaves the level loop at libs/ogs/ogsCrystalRouter.cpp:455-466 before the
+    forwarding exchange its partner in the lower half still posts at :505-514.)"""
     ng = _ogs_check(need(os.path.join(SERIAL, "ogs_check")), ranks, ["-nx", "3", "-ny", "3", "-nz", "2", "-p", "4"], mode=["-m", "Serial"])
     # global nodes of the mesh: the process grid multiplies the per-rank box (libs/mesh/meshSetupBoxHex3D.cpp)
     grid = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1)}[ranks]
@@ -135,3 +140,15 @@ def test_reference_ogs_device_path_equals_its_host_path_on_the_b200(ranks):
     exe = need(os.path.join(DRV, "ogs_check"))
     _ogs_check(exe, ranks, ["-nx", "6", "-ny", "5", "-nz", "4", "-p", "7"])
     _ogs_check(exe, ranks, ["-nx", "3", "-ny", "2", "-nz", "2", "-p", "1"])
+
+
+def test_reference_device_gather_scatter_ignores_the_op():
+    """A quirk of the reference the check exposes: ogsOperator_t::GatherScatter(deviceMemory) launches
+    gatherScatterKernel[type][Add] for every op (libs/ogs/ogsOperator.cpp:443-480), so its device and host paths differ for
+    Mul / Max / Min on the interior rows — on its own Serial backend, no kernel of ours involved.  The native layer
+    (streamparanumal_b200/host) honours the op, as the reference's host path and its header (include/ogs.hpp:75-90) do."""
+    exe = need(os.path.join(SERIAL, "ogs_check"))
+    env = dict(os.environ, OGS_CHECK_ALL_OPS="1")
+    r = subprocess.run([exe, "-m", "Serial", "-nx", "2", "-ny", "2", "-nz", "2", "-p", "2"], capture_output=True, text=True, env=env, timeout=600)
+    m = re.search(CHECK_LINE, r.stdout)
+    assert m and int(m.group(5)) > 0 and (int(m.group(6)), int(m.group(7))) == (0, 0), r.stdout
