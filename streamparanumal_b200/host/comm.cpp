@@ -12,6 +12,7 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <functional>
 #include <thread>
@@ -221,7 +222,16 @@ void comm_t::alltoallv_bytes(const void* sbuf, const size_t* sc, const size_t* s
   char* r = static_cast<char*>(rbuf);
   const int P = size(), me = rank();
   SPN_ABORT("alltoallv self size mismatch", sc[me] != rc[me]);
-  if (sc[me]) memcpy(r + ro[me], s + so[me], sc[me]);
+  if (sc[me] >= ((size_t)16 << 20)) {  // the self part of the setup's label routing is hundreds of MB: copy (and first-touch) it in parallel
+    const size_t piece = (size_t)4 << 20, pieces = (sc[me] + piece - 1) / piece;
+#pragma omp parallel for schedule(static)
+    for (size_t c = 0; c < pieces; ++c) {
+      const size_t lo = c * piece, len = std::min(piece, sc[me] - lo);
+      memcpy(r + ro[me] + lo, s + so[me] + lo, len);
+    }
+  } else if (sc[me]) {
+    memcpy(r + ro[me], s + so[me], sc[me]);
+  }
   for (int step = 1; step < P; ++step) {
     const int dst = (me + step) % P, src = (me - step + P) % P;
     sendrecv(dst, s + so[dst], sc[dst], src, r + ro[src], rc[src]);

@@ -194,17 +194,25 @@ void parallel_fill(T* v, size_t n, T value) {
 // entries: signed labels `ids` at columns `cols` (cols strictly ascending).
 // Rows = label groups in first-appearance order, groups with a positive copy first (libs/ogs/ogsSetup.cpp:492-559);
 // columns ascend inside a row (stable SortByRow, :561-579).  Every pass is a parallel loop or a prefix sum.
-std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const hvec<hlong>& ids, const hvec<dlong>& cols) {
+// `sorted`: the entries already sorted by (|label|, entry) — on one rank the directory round has just produced exactly
+// that order for the same entries, so the local operator does not sort again.
+std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const hvec<hlong>& ids, const hvec<dlong>& cols,
+                                              hvec<Key>* sorted = nullptr) {
   auto op = std::make_shared<ogsOperator_t>();
   op->kind = (kind == Unsigned) ? Unsigned : Signed;
   op->Ncols = Ncols;
   const dlong n = (dlong)ids.size();
   op->nnzT = n;
 
-  hvec<Key> keys((size_t)n);
+  hvec<Key> keys;
+  if (sorted && (dlong)sorted->size() == n) {
+    keys.swap(*sorted);
+  } else {
+    keys.resize((size_t)n);
 #pragma omp parallel for
-  for (dlong i = 0; i < n; ++i) keys[i] = Key{habs(ids[i]), i};
-  sort_keys_by_label(keys);  // groups contiguous, members in ascending entry (= column) order
+    for (dlong i = 0; i < n; ++i) keys[i] = Key{habs(ids[i]), i};
+    sort_keys_by_label(keys);  // groups contiguous, members in ascending entry (= column) order
+  }
 
   // group starts in sorted order
   hvec<dlong> groupOfSorted((size_t)n);  // first: 1 at a group start, then the group index
@@ -695,6 +703,9 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
       }
     }
   }
+  // one rank: receive slot i is entry i and nothing is shared, so these keys are the local operator's (see build_operator)
+  hvec<Key> localSorted;
+  if (size == 1) localSorted.swap(keys);
   keys.clear();
   keys.shrink_to_fit();
   groupStart.clear();
@@ -768,7 +779,7 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   baseIds.clear(); baseIds.shrink_to_fit();
   colIds.clear(); colIds.shrink_to_fit();
   phase.lap("split local / halo");
-  gatherLocal = build_operator(kind, N, localIds, localCols);
+  gatherLocal = build_operator(kind, N, localIds, localCols, size == 1 ? &localSorted : nullptr);
   phase.lap("local operator");
   gatherHalo = build_operator(kind, N, haloIds, haloCols);
   NlocalT = gatherLocal->NrowsT;
