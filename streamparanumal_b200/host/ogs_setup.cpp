@@ -504,7 +504,11 @@ void ogs_t::Setup(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_, co
     SPN_CHECK(spn_event_create(&joinEvent));
     SPN_CHECK(spn_event_create(&packedEvent));
     SPN_CHECK(spn_event_create(&recvEvent));
-    comm.device();  // NCCL communicator: collective, every rank reaches this point
+    // NCCL communicator: collective, every rank reaches this point.  SPN_OGS_NCCL=lazy leaves it to the first call that
+    // sends over NCCL (StartExchange, also reached by every rank): ranks that share one GPU — the oversubscribed
+    // peer-memory tests — cannot form an NCCL communicator and never need one.
+    const char* ncclMode = getenv("SPN_OGS_NCCL");
+    if (!(ncclMode && std::string(ncclMode) == "lazy")) comm.device();
     SetupPeerExchange();
   }
   AllocBuffer(sizeof(dfloat));

@@ -133,10 +133,9 @@ def test_ogs_check_is_sound_on_the_reference_serial_backend(ranks):
 def test_reference_ogs_device_path_equals_its_host_path_on_the_b200(ranks):
     """the reference's mesh_t + ogs_t, unchanged, on the sm_100a backend: GatherScatter / Gather / Scatter on device memory
     (ogsOperator_t -> kernel_t -> C ABI; at P > 1 the reference's own pairwise exchange over the MPI stand-in, one GPU per
-    rank) equal the reference's host-memory overloads bit for bit"""
-    import torch
-    if torch.cuda.device_count() < ranks:
-        pytest.skip(f"needs {ranks} GPUs, box has {torch.cuda.device_count()}")
+    rank where the box has them) equal the reference's host-memory overloads bit for bit"""
+    # fewer GPUs than ranks: the reference's own platform_t shares them (device_id % deviceCount with its oversubscription
+    # warning, libs/core/platformDeviceConfig.cpp:88-95); its exchange is host-staged MPI, so nothing spins on the device
     exe = need(os.path.join(DRV, "ogs_check"))
     _ogs_check(exe, ranks, ["-nx", "6", "-ny", "5", "-nz", "4", "-p", "7"])
     _ogs_check(exe, ranks, ["-nx", "3", "-ny", "2", "-nz", "2", "-p", "1"])
