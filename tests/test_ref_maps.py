@@ -57,6 +57,19 @@ def test_native_maps_equal_reference_setup(name, golden, comm):
     assert np.array_equal(o.ids, golden[f"{name}/ids_out"]), f"{name}: signs written back differ from the reference's pick"
 
 
+@pytest.mark.parametrize("threads", ["1", "3", "13"])
+def test_setup_does_not_depend_on_the_thread_count(threads, golden, comm, monkeypatch):
+    """the setup's order-preserving parallel passes (chunked selections, the skip-ahead generator of the positive pick, the
+    radix sort) give the reference's maps and picks for any number of threads — including more chunks than label groups"""
+    monkeypatch.setenv("SPN_SETUP_THREADS", threads)
+    for name in ("hex_p3_nx4", "hex_p7_nx2", "hex_p7_masked", "random_labels", "long_rows"):
+        o = _native(name, comm, order=1)
+        for k in ("rowStartsT", "colIdsT", "rowStartsN", "colIdsN"):
+            ref = golden[f"{name}/{k}"]
+            assert np.array_equal(o.array("local_" + k)[: ref.size], ref), f"{name}: {k} with {threads} threads"
+        assert np.array_equal(o.ids, golden[f"{name}/ids_out"]), f"{name}: pick with {threads} threads"
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_stable_pick_order_changes_only_the_positive_copy(name, golden, comm):
     """default order of a label's copies: same T maps and counts; N maps name one (possibly other) copy of each row"""
