@@ -18,3 +18,23 @@ def test_host_layer_handle_semantics(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "host handle semantics ok" in r.stdout
+
+
+def test_mpi_stand_in_semantics(tmp_path):
+    """tests/cpp/test_mpi_shim.cpp under spnrun at 1, 2, 3, 5 ranks: ordering of same-tag messages of different sizes,
+    zero-length and 24 MB messages, separate communicators, ragged collectives, rank-ordered reductions — what the
+    reference's comm_t / ogs setup assume of MPI and the multi-rank pins (tests/test_ref_multirank_cpu.py) rest on."""
+    import pytest
+    exe = str(tmp_path / "test_mpi_shim")
+    cmd = ["g++", "-O1", "-std=c++17", "-Wall", f"-I{ROOT}/include/shim", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_mpi_shim.cpp"),
+           os.path.join(ROOT, "streamparanumal_b200", "shim", "mpi_shim.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    spnrun = os.path.join(ROOT, "streamparanumal_b200", "bin", "spnrun")
+    if not os.access(spnrun, os.X_OK):
+        pytest.fail("streamparanumal_b200/bin/spnrun missing: run `make` first")
+    for ranks in (1, 2, 3, 5):
+        cmdline = [exe] if ranks == 1 else [spnrun, "-np", str(ranks), exe]
+        r = subprocess.run(cmdline, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert f"mpi shim ok ({ranks} ranks)" in r.stdout
