@@ -38,3 +38,15 @@ def test_mpi_stand_in_semantics(tmp_path):
         r = subprocess.run(cmdline, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
         assert f"mpi shim ok ({ranks} ranks)" in r.stdout
+
+
+def test_occa_stand_in_semantics(tmp_path):
+    """tests/cpp/test_occa_shim.cpp: include/shim/occa.hpp against a recording back end — json paths, malloc / slicing /
+    copies with their kinds, offsets and async flags, null handles, stream switching, kernel argument packing
+    (the OCCA surface of SURVEY.md section 8b)."""
+    exe = str(tmp_path / "test_occa_shim")
+    cmd = ["g++", "-O1", "-std=c++17", "-Wall", f"-I{ROOT}/include/shim", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_occa_shim.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "occa shim ok" in r.stdout, r.stdout + r.stderr
