@@ -225,15 +225,17 @@ double ref_ogs_time_gather_scatter(void* handle, int path, int steps, int warmup
   return ElapsedTime(t0, t1) / (steps > 0 ? steps : 1);
 }
 
-// global node ids of the reference's own box mesh of degree-p hex elements (one rank): ids_out has nx*ny*nz*(p+1)^3
-// entries; returns the number of entries written, or -1 when the buffer is too small
-long long ref_mesh_box_hex_ids(int nx, int ny, int nz, int p, long long* ids_out, long long capacity) {
+// global node ids of the reference's own box mesh (one rank) of degree-p elements of type `element` ("Tri", "Quad", "Tet",
+// "Hex": libs/mesh/meshSetupBox{Tri2D,Quad2D,Tet3D,Hex3D}.cpp + meshConnectNodes.cpp): Nelements*Np entries.
+// Returns the number of entries; writes them when ids_out is non-null and capacity suffices, else writes nothing
+// (-1 when a non-null buffer is too small).  nz is ignored by the 2-D element types.
+long long ref_mesh_box_ids(const char* element, int nx, int ny, int nz, int p, long long* ids_out, long long capacity) {
   settings_t settings(env().comm);
   platformAddSettings(settings);
   meshAddSettings(settings);
   settings.newSetting("-v", "--verbose", "VERBOSE", "FALSE", "Enable verbose output", {"TRUE", "FALSE"});  // as the BS drivers do
   settings.changeSetting("THREAD MODEL", "Serial");
-  settings.changeSetting("ELEMENT TYPE", "Hex");
+  settings.changeSetting("ELEMENT TYPE", element);
   settings.changeSetting("BOX NX", std::to_string(nx));
   settings.changeSetting("BOX NY", std::to_string(ny));
   settings.changeSetting("BOX NZ", std::to_string(nz));
@@ -241,9 +243,13 @@ long long ref_mesh_box_hex_ids(int nx, int ny, int nz, int p, long long* ids_out
   platform_t platform(settings);
   mesh_t mesh(platform, settings, env().comm);
   const long long n = (long long)mesh.Nelements * mesh.Np;
+  if (!ids_out) return n;
   if (n > capacity) return -1;
   memcpy(ids_out, mesh.globalIds.ptr(), sizeof(hlong) * (size_t)n);
   return n;
+}
+long long ref_mesh_box_hex_ids(int nx, int ny, int nz, int p, long long* ids_out, long long capacity) {
+  return ref_mesh_box_ids("Hex", nx, ny, nz, p, ids_out, capacity);
 }
 
 }  // extern "C"

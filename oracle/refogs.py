@@ -45,6 +45,8 @@ def lib():
         l.ref_halo_apply.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int]
         l.ref_mesh_box_hex_ids.restype = c_longlong
         l.ref_mesh_box_hex_ids.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_longlong]
+        l.ref_mesh_box_ids.restype = c_longlong
+        l.ref_mesh_box_ids.argtypes = [ctypes.c_char_p, c_int, c_int, c_int, c_int, c_void_p, c_longlong]
         _lib = l
     return _lib
 
@@ -152,5 +154,16 @@ def mesh_box_hex_ids(nx, ny, nz, p):
     n = nx * ny * nz * (p + 1) ** 3
     ids = np.empty(n, dtype=np.int64)
     got = lib().ref_mesh_box_hex_ids(nx, ny, nz, p, ids.ctypes.data, n)
+    assert got == n, got
+    return ids
+
+
+def mesh_box_ids(element, nx, ny, nz, p):
+    """globalIds of the reference's own box mesh of `element` in {"Tri", "Quad", "Tet", "Hex"} at one rank
+    (libs/mesh/meshSetupBox*.cpp + meshConnectNodes.cpp:44-81)"""
+    n = lib().ref_mesh_box_ids(element.encode(), nx, ny, nz, p, None, 0)
+    assert n > 0, n
+    ids = np.empty(n, dtype=np.int64)
+    got = lib().ref_mesh_box_ids(element.encode(), nx, ny, nz, p, ids.ctypes.data, n)
     assert got == n, got
     return ids

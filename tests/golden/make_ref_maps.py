@@ -11,14 +11,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from golden.ref_map_cases import CASES, case_ids, case_values  # noqa: E402
+from golden.ref_map_cases import CASES, REF_MESHES, case_ids, case_values  # noqa: E402
 from oracle import refogs  # noqa: E402
 
 
 def main():
     out = {}
     for name in CASES:
-        ids, kind, unique = case_ids(name)
+        if name in REF_MESHES:  # labels of the reference's own Tri / Quad / Tet box mesh, signs dropped
+            ids, kind, unique = np.abs(refogs.mesh_box_ids(*REF_MESHES[name])), refogs.SIGNED, True
+            out[f"{name}/ids_in"] = ids.copy()
+        else:
+            ids, kind, unique = case_ids(name)
         r = refogs.RefOgs(ids, kind=kind, unique=unique)
         for k, v in r.maps().items():
             out[f"{name}/{k}"] = v
