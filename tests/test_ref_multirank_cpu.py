@@ -23,7 +23,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, tmpdir, nx, ny, nz, p):
+def _worker(rank, world, port, tmpdir, nx, ny, nz, p, element="Hex"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SPN_RANK=str(rank), SPN_SIZE=str(world),
@@ -35,7 +35,14 @@ def _worker(rank, world, port, tmpdir, nx, ny, nz, p):
         from oracle import refogs
         from streamparanumal_b200 import host
         comm = host.Comm(rank, world, rendezvous=tmpdir)
-        ids, nglobal = host.box_hex_ids(rank, world, nx, ny, nz, p)
+        if element == "Hex":
+            ids, nglobal = host.box_hex_ids(rank, world, nx, ny, nz, p)
+        else:
+            # the reference's own partitioned Tri / Quad / Tet box mesh, built by its mesh library across the P ranks
+            ids = np.abs(refogs.mesh_box_ids(element, nx, ny, nz, p))
+            mine = [None] * world
+            dist.all_gather_object(mine, np.unique(ids))
+            nglobal = np.unique(np.concatenate(mine)).size
         # the reference, as rank `rank` of `world`
         ref = refogs.RefOgs(ids, kind=refogs.SIGNED, unique=True)
         # the native plan, copies of a label in the order the serial reference build leaves them
@@ -130,6 +137,16 @@ def test_native_plan_equals_reference_ogs_at_p_ranks(world, nx, ny, nz, p):
         pytest.skip("oracle/_ref/libref_ogs.so not built here (needs /root/reference)")
     with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
         mp.spawn(_worker, args=(world, _free_port(), tmpdir, nx, ny, nz, p), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("world,element,nx,ny,nz,p", [(2, "Tet", 2, 2, 2, 3), (4, "Tri", 3, 3, 1, 4), (2, "Quad", 3, 2, 1, 5)])
+def test_native_plan_equals_reference_ogs_on_its_other_meshes(world, element, nx, ny, nz, p):
+    """same pins on the labels of the reference's partitioned Tri / Quad / Tet box meshes (its mesh library running on the P ranks)"""
+    from oracle import refogs
+    if not refogs.available():
+        pytest.skip("oracle/_ref/libref_ogs.so not built here (needs /root/reference)")
+    with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
+        mp.spawn(_worker, args=(world, _free_port(), tmpdir, nx, ny, nz, p, element), nprocs=world, join=True)
 
 
 @pytest.mark.parametrize("world,K,dtype", [(2, 1, "float64"), (3, 2, "float64"), (4, 1, "int32"), (3, 3, "float32")])
