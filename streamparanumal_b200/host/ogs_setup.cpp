@@ -645,7 +645,9 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   emit_selected(recvN, chunks, groupOffsets, opens_group, [&](dlong i, dlong g) { groupStart[g] = i; });
   groupStart[Ngroups] = recvN;
 
-  hvec<int> recvShared((size_t)recvN);
+  // what travels back to the sources: one byte per copy, bit 0 = label shared between ranks, bit 1 = positive copy
+  // (the reference returns the signed label and a flag, 12 bytes per copy: libs/ogs/ogsSetup.cpp:384-425)
+  hvec<unsigned char> recvAnswer((size_t)recvN);
   hvec<char> groupShared((size_t)Ngroups);  // copies on more than one rank
   int is_unique = 1;
   // every group is independent once its draw is known: thread chunks of consecutive groups, the generator skipped
@@ -657,22 +659,24 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
     if (unique) lcg.skip((unsigned long long)g0);
     for (dlong g = g0; g < g1; ++g) {
       const dlong s0 = groupStart[g], e = groupStart[g + 1];
-      const hlong label = keys[s0].label;
+      // members are in ascending receive slot = ascending source rank: first and last differ iff the label is shared
+      const unsigned char shared = (size > 1 && rank_of(keys[s0].idx) != rank_of(keys[e - 1].idx)) ? 1 : 0;
+      groupShared[g] = (char)shared;
       if (unique) {
         // one positive copy per label (libs/ogs/ogsSetup.cpp:364-382)
         const int m = lcg.next() % (int)(e - s0);
-        for (dlong i = s0; i < e; ++i) recvLabels[keys[i].idx] = -label;
+        for (dlong i = s0; i < e; ++i) recvAnswer[keys[i].idx] = shared;
         const dlong picked = refOrder.empty() ? keys[s0 + m].idx : refOrder[(size_t)(s0 + m)].second;
-        recvLabels[picked] = label;
+        recvAnswer[picked] = shared | 2;
       } else {
         int positives = 0;
-        for (dlong i = s0; i < e; ++i) positives += (recvLabels[keys[i].idx] > 0) ? 1 : 0;
+        for (dlong i = s0; i < e; ++i) {
+          const int pos = (recvLabels[keys[i].idx] > 0) ? 1 : 0;
+          positives += pos;
+          recvAnswer[keys[i].idx] = (unsigned char)(shared | (pos << 1));
+        }
         if (positives != 1) is_unique = 0;
       }
-      // members are in ascending receive slot = ascending source rank: first and last differ iff the label is shared
-      const int shared = (size > 1 && rank_of(keys[s0].idx) != rank_of(keys[e - 1].idx)) ? 1 : 0;
-      groupShared[g] = (char)shared;
-      for (dlong i = s0; i < e; ++i) recvShared[keys[i].idx] = shared;
     }
   }
 
@@ -695,7 +699,7 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
         const int r = rank_of(keys[i].idx);
         int pos = 0;
         dlong j = i;
-        for (; j < e && rank_of(keys[j].idx) == r; ++j) pos |= (recvLabels[keys[j].idx] > 0) ? 1 : 0;
+        for (; j < e && rank_of(keys[j].idx) == r; ++j) pos |= (recvAnswer[keys[j].idx] >> 1) & 1;
         sharers.push_back((hlong)r * 2 + pos);
         i = j;
       }
@@ -727,22 +731,22 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   }
 
   // answers back to the sources
-  hvec<int> sharedOfSlot((size_t)Nids);
-  comm.Alltoallv(recvShared.data(), recvCounts.data(), recvOffsets.data(), sharedOfSlot.data(), sendCounts.data(),
-                 sendOffsets.data());
+  recvLabels.clear();
+  recvLabels.shrink_to_fit();
+  sendLabels.clear();
+  sendLabels.shrink_to_fit();
+  hvec<unsigned char> slotAnswer((size_t)Nids);
+  comm.Alltoallv(recvAnswer.data(), recvCounts.data(), recvOffsets.data(), slotAnswer.data(), sendCounts.data(), sendOffsets.data());
+  recvAnswer.clear();
+  recvAnswer.shrink_to_fit();
   if (unique) {
-    comm.Alltoallv(recvLabels.data(), recvCounts.data(), recvOffsets.data(), sendLabels.data(), sendCounts.data(),
-                   sendOffsets.data());
 #pragma omp parallel for
     for (dlong n = 0; n < Nids; ++n) {
-      baseIds[n] = sendLabels[sendPos[n]];
+      const hlong label = habs(baseIds[n]);
+      baseIds[n] = (slotAnswer[sendPos[n]] & 2) ? label : -label;
       ids[colIds[n]] = baseIds[n];  // write the signs back (libs/ogs/ogsSetup.cpp:147-150)
     }
   }
-  recvLabels.clear();
-  recvLabels.shrink_to_fit();
-  recvShared.clear();
-  recvShared.shrink_to_fit();
 
   // sharer lists of the shared labels this rank holds
   std::vector<hlong> sharerStream;
@@ -765,8 +769,8 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   hvec<hlong> localIds, haloIds;
   hvec<dlong> localCols, haloCols;
   {
-    auto is_halo = [&](dlong n) { return sharedOfSlot[sendPos[n]] != 0; };
-    auto is_local = [&](dlong n) { return sharedOfSlot[sendPos[n]] == 0; };
+    auto is_halo = [&](dlong n) { return (slotAnswer[sendPos[n]] & 1) != 0; };
+    auto is_local = [&](dlong n) { return (slotAnswer[sendPos[n]] & 1) == 0; };
     const std::vector<dlong> haloOffsets = count_selected(Nids, chunks, is_halo);
     std::vector<dlong> localOffsets((size_t)chunks + 1);
     for (int c = 0; c <= chunks; ++c) localOffsets[c] = chunk_lo(Nids, c, chunks) - haloOffsets[c];
@@ -778,8 +782,7 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
     emit_selected(Nids, chunks, localOffsets, is_local, [&](dlong n, dlong q) { localIds[q] = baseIds[n]; localCols[q] = colIds[n]; });
   }
   sendPos.clear(); sendPos.shrink_to_fit();
-  sendLabels.clear(); sendLabels.shrink_to_fit();
-  sharedOfSlot.clear(); sharedOfSlot.shrink_to_fit();
+  slotAnswer.clear(); slotAnswer.shrink_to_fit();
   baseIds.clear(); baseIds.shrink_to_fit();
   colIds.clear(); colIds.shrink_to_fit();
   phase.lap("split local / halo");
