@@ -214,20 +214,13 @@ std::shared_ptr<ogsOperator_t> build_operator(Kind kind, dlong Ncols, const hvec
     sort_keys_by_label(keys);  // groups contiguous, members in ascending entry (= column) order
   }
 
-  // group starts in sorted order
-  hvec<dlong> groupOfSorted((size_t)n);  // first: 1 at a group start, then the group index
-#pragma omp parallel for
-  for (dlong i = 0; i < n; ++i) groupOfSorted[i] = (i == 0 || keys[i].label != keys[i - 1].label) ? 1 : 0;
-  const dlong NT = n ? exclusive_scan(groupOfSorted.data(), (size_t)n) : 0;  // groupOfSorted[i] = groups before i ...
-#pragma omp parallel for
-  for (dlong i = 0; i < n; ++i)  // ... make it the group OF i: a start belongs to the group it opens
-    if (i == 0 || keys[i].label != keys[i - 1].label) groupOfSorted[i] += 1;
-#pragma omp parallel for
-  for (dlong i = 0; i < n; ++i) groupOfSorted[i] -= 1;
-  hvec<dlong> groupStart((size_t)NT + 1);  // sorted position of the first member
-#pragma omp parallel for
-  for (dlong i = 0; i < n; ++i)
-    if (i == 0 || groupOfSorted[i] != groupOfSorted[i - 1]) groupStart[groupOfSorted[i]] = i;
+  // label groups = runs of equal labels in sorted order; groupStart[g] = sorted position of the first member
+  const int chunks = std::max(1, omp_get_max_threads()) * 4;
+  auto opens_group = [&](dlong i) { return i == 0 || keys[i].label != keys[i - 1].label; };
+  const std::vector<dlong> groupOffsets = count_selected(n, chunks, opens_group);
+  const dlong NT = groupOffsets[chunks];
+  hvec<dlong> groupStart((size_t)NT + 1);
+  emit_selected(n, chunks, groupOffsets, opens_group, [&](dlong i, dlong g) { groupStart[g] = i; });
   groupStart[NT] = n;
   hvec<char> groupPos((size_t)NT);  // has a positive copy on this rank
 #pragma omp parallel for
@@ -578,10 +571,17 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   // ---- 1. directory round ------------------------------------------------------------------
   // label L lives on directory rank |L| % size; the send buffer is ordered by destination, entries of one destination
   // in column order (per-chunk histograms, destination-major / chunk-minor offsets)
+  // On ONE rank the round is the identity (receive slot i = entry i): nothing is routed, copied or indexed through sendPos.
+  const bool single = (size == 1);
   std::vector<int> sendCounts(size, 0), sendOffsets(size + 1, 0), recvCounts(size, 0), recvOffsets(size + 1, 0);
-  hvec<dlong> sendPos((size_t)Nids);  // entry n sits at slot sendPos[n] of the send buffer (stable by dest)
-  hvec<hlong> sendLabels((size_t)Nids);
-  {
+  hvec<dlong> sendPos;  // entry n sits at slot sendPos[n] of the send buffer (stable by dest)
+  hvec<hlong> sendLabels, recvLabels;
+  if (single) {
+    sendCounts[0] = recvCounts[0] = Nids;
+    sendOffsets[1] = recvOffsets[1] = Nids;
+  } else {
+    sendPos.resize((size_t)Nids);
+    sendLabels.resize((size_t)Nids);
     std::vector<dlong> hist((size_t)chunks * size, 0);
 #pragma omp parallel for schedule(static, 1)
     for (int c = 0; c < chunks; ++c) {
@@ -608,19 +608,23 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
         sendLabels[pos] = baseIds[n];
       }
     }
+    comm.Alltoall(sendCounts.data(), recvCounts.data());
+    for (int r = 0; r < size; ++r) recvOffsets[r + 1] = recvOffsets[r] + recvCounts[r];
+    recvLabels.resize((size_t)recvOffsets[size]);
+    comm.Alltoallv(sendLabels.data(), sendCounts.data(), sendOffsets.data(), recvLabels.data(), recvCounts.data(),
+                   recvOffsets.data());
+    sendLabels.clear();
+    sendLabels.shrink_to_fit();
   }
-  comm.Alltoall(sendCounts.data(), recvCounts.data());
-  for (int r = 0; r < size; ++r) recvOffsets[r + 1] = recvOffsets[r] + recvCounts[r];
   const dlong recvN = recvOffsets[size];
-  hvec<hlong> recvLabels((size_t)recvN);
-  comm.Alltoallv(sendLabels.data(), sendCounts.data(), sendOffsets.data(), recvLabels.data(), recvCounts.data(),
-                 recvOffsets.data());
+  const hlong* recvL = single ? baseIds.data() : recvLabels.data();  // label of every receive slot (read only)
+  auto slot_of = [&](dlong n) { return single ? n : sendPos[n]; };
 
   phase.lap("route labels to directory ranks");
   // group the received copies by |label|; inside a group they stay in (source rank, source order)
   hvec<Key> keys((size_t)recvN);
 #pragma omp parallel for
-  for (dlong i = 0; i < recvN; ++i) keys[i] = Key{habs(recvLabels[i]), i};
+  for (dlong i = 0; i < recvN; ++i) keys[i] = Key{habs(recvL[i]), i};
   sort_keys_by_label(keys);
   phase.lap("sort received labels");
   auto rank_of = [&](dlong idx) {  // source rank of receive slot idx
@@ -632,7 +636,7 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   std::vector<std::pair<hlong, dlong>> refOrder;  // pick mode 1: (|label|, receive slot) as std::sort leaves them
   if (unique && pick_mode() == 1) {
     refOrder.resize((size_t)recvN);
-    for (dlong i = 0; i < recvN; ++i) refOrder[i] = {habs(recvLabels[i]), i};
+    for (dlong i = 0; i < recvN; ++i) refOrder[i] = {habs(recvL[i]), i};
     std::sort(refOrder.begin(), refOrder.end(),
               [](const std::pair<hlong, dlong>& a, const std::pair<hlong, dlong>& b) { return a.first < b.first; });
   }
@@ -671,7 +675,7 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
       } else {
         int positives = 0;
         for (dlong i = s0; i < e; ++i) {
-          const int pos = (recvLabels[keys[i].idx] > 0) ? 1 : 0;
+          const int pos = (recvL[keys[i].idx] > 0) ? 1 : 0;
           positives += pos;
           recvAnswer[keys[i].idx] = (unsigned char)(shared | (pos << 1));
         }
@@ -733,17 +737,20 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   // answers back to the sources
   recvLabels.clear();
   recvLabels.shrink_to_fit();
-  sendLabels.clear();
-  sendLabels.shrink_to_fit();
-  hvec<unsigned char> slotAnswer((size_t)Nids);
-  comm.Alltoallv(recvAnswer.data(), recvCounts.data(), recvOffsets.data(), slotAnswer.data(), sendCounts.data(), sendOffsets.data());
-  recvAnswer.clear();
-  recvAnswer.shrink_to_fit();
+  hvec<unsigned char> slotAnswer;
+  if (single) {
+    slotAnswer.swap(recvAnswer);
+  } else {
+    slotAnswer.resize((size_t)Nids);
+    comm.Alltoallv(recvAnswer.data(), recvCounts.data(), recvOffsets.data(), slotAnswer.data(), sendCounts.data(), sendOffsets.data());
+    recvAnswer.clear();
+    recvAnswer.shrink_to_fit();
+  }
   if (unique) {
 #pragma omp parallel for
     for (dlong n = 0; n < Nids; ++n) {
       const hlong label = habs(baseIds[n]);
-      baseIds[n] = (slotAnswer[sendPos[n]] & 2) ? label : -label;
+      baseIds[n] = (slotAnswer[slot_of(n)] & 2) ? label : -label;
       ids[colIds[n]] = baseIds[n];  // write the signs back (libs/ogs/ogsSetup.cpp:147-150)
     }
   }
@@ -768,9 +775,12 @@ void ogs_t::SetupPlan(const dlong N_, hlong* ids, comm_t comm_, const Kind kind_
   // ---- 2. split into local / halo entries and number the rows ---------------------------------
   hvec<hlong> localIds, haloIds;
   hvec<dlong> localCols, haloCols;
-  {
-    auto is_halo = [&](dlong n) { return (slotAnswer[sendPos[n]] & 1) != 0; };
-    auto is_local = [&](dlong n) { return (slotAnswer[sendPos[n]] & 1) == 0; };
+  if (single) {  // nothing is shared: every entry is local, in place
+    localIds.swap(baseIds);
+    localCols.swap(colIds);
+  } else {
+    auto is_halo = [&](dlong n) { return (slotAnswer[slot_of(n)] & 1) != 0; };
+    auto is_local = [&](dlong n) { return (slotAnswer[slot_of(n)] & 1) == 0; };
     const std::vector<dlong> haloOffsets = count_selected(Nids, chunks, is_halo);
     std::vector<dlong> localOffsets((size_t)chunks + 1);
     for (int c = 0; c <= chunks; ++c) localOffsets[c] = chunk_lo(Nids, c, chunks) - haloOffsets[c];
