@@ -37,6 +37,15 @@ def _worker(rank, world, port, tmpdir, nx, ny, nz, p, element="Hex"):
         comm = host.Comm(rank, world, rendezvous=tmpdir)
         if element == "Hex":
             ids, nglobal = host.box_hex_ids(rank, world, nx, ny, nz, p)
+        elif element.startswith("Random"):
+            # no mesh: nx nodes per rank (ragged: rank r gets nx * (r + 1) / 2) over a common pool of ny labels, so labels have
+            # several copies on one rank AND on several ranks; every 11th node masked; seed p
+            rng = np.random.RandomState(1000 * p + rank)
+            ids = rng.randint(1, ny + 1, size=nx * (rank + 1) // 2).astype(np.int64)
+            ids[::11] = 0
+            mine = [None] * world
+            dist.all_gather_object(mine, np.unique(ids[ids != 0]))
+            nglobal = np.unique(np.concatenate(mine)).size
         else:
             # the reference's own partitioned Tri / Quad / Tet box mesh, built by its mesh library across the P ranks
             ids = np.abs(refogs.mesh_box_ids(element, nx, ny, nz, p))
@@ -147,6 +156,17 @@ def test_native_plan_equals_reference_ogs_on_its_other_meshes(world, element, nx
         pytest.skip("oracle/_ref/libref_ogs.so not built here (needs /root/reference)")
     with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
         mp.spawn(_worker, args=(world, _free_port(), tmpdir, nx, ny, nz, p, element), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("world,nodes,labels,seed", [(3, 400, 150, 1), (5, 300, 700, 2), (2, 50, 400, 3), (4, 1000, 60, 4)])
+def test_native_plan_equals_reference_ogs_on_random_labels(world, nodes, labels, seed):
+    """unstructured sharing: labels with several copies per rank on several ranks, ranks of different sizes, labels held by
+    one rank only, masked nodes — 2 to 5 ranks (the Pairwise method the capi asks for works at any rank count)"""
+    from oracle import refogs
+    if not refogs.available():
+        pytest.skip("oracle/_ref/libref_ogs.so not built here (needs /root/reference)")
+    with tempfile.TemporaryDirectory(prefix="spn_rdv_") as tmpdir:
+        mp.spawn(_worker, args=(world, _free_port(), tmpdir, nodes, labels, 0, seed, "Random"), nprocs=world, join=True)
 
 
 @pytest.mark.parametrize("world,K,dtype", [(2, 1, "float64"), (3, 2, "float64"), (4, 1, "int32"), (3, 3, "float32")])
