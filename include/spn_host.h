@@ -67,6 +67,8 @@ int spn_host_ogs_exchange_info(spn_host_ogs_t ogs, int mode, long long* info);
  *           15 cmbStarts 16 cmbIds 17 recvRows 18 rowSendStarts 19 rowSendDst 20 slotDst (peer-memory pack: send slots per halo row) */
 int spn_host_ogs_array(spn_host_ogs_t ogs, int which, int mode, const int** ptr, long long* len);
 int spn_host_ogs_halo_labels(spn_host_ogs_t ogs, const long long** ptr, long long* len);  /* |label| of every halo row */
+/* ogs_t::SetupGlobalToLocalMapping (libs/ogs/ogsSetup.cpp:833-849): out[N] = row of every node in a gathered vector, -1 = masked */
+int spn_host_ogs_global_to_local(spn_host_ogs_t ogs, int* out);
 
 /* device operations on raw device pointers; type = spn_type, op = spn_op, trans: 0 Sym 1 NoTrans 2 Trans.
  * Kernels go to the platform's current stream (spn_host_platform_set_stream). */

@@ -107,6 +107,14 @@ const int* ref_ogs_array(void* handle, const char* name, long long* len) {
   return m.ptr();
 }
 
+// ogs_t::SetupGlobalToLocalMapping (libs/ogs/ogsSetup.cpp:833-849): out has N entries
+void ref_ogs_global_to_local(void* handle, int* out) {
+  Handle* h = static_cast<Handle*>(handle);
+  memory<dlong> g2l(h->ogs.N > 0 ? h->ogs.N : 1);
+  h->ogs.SetupGlobalToLocalMapping(g2l);
+  for (dlong n = 0; n < h->ogs.N; ++n) out[n] = g2l[n];
+}
+
 // host-memory overloads (libs/ogs/ogs.cpp:127-204, 303-393, 494-578): type 0..3 = float, double, int, long long
 #define BY_TYPE(type, ...)                              \
   switch (type) {                                       \

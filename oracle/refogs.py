@@ -43,6 +43,7 @@ def lib():
         l.ref_halo_destroy.argtypes = [c_void_p]
         l.ref_halo_nhalo.argtypes = [c_void_p]
         l.ref_halo_apply.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int]
+        l.ref_ogs_global_to_local.argtypes = [c_void_p, c_void_p]
         l.ref_mesh_box_hex_ids.restype = c_longlong
         l.ref_mesh_box_hex_ids.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_longlong]
         l.ref_mesh_box_ids.restype = c_longlong
@@ -63,6 +64,11 @@ class RefOgs:
         lib().ref_ogs_dims(self._h, d)
         (self.N, self.Ngather, self.NlocalT, self.NlocalP, self.NhaloT, self.NhaloP, self.nnzT, self.nnzN,
          self.NrowBlocksT, self.NrowBlocksN, self.NgatherGlobal) = list(d)[:11]
+
+    def global_to_local(self):
+        out = np.empty(self.N, dtype=np.int32)
+        lib().ref_ogs_global_to_local(self._h, out.ctypes.data)
+        return out
 
     def array(self, name):
         n = c_longlong()

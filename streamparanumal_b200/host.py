@@ -41,6 +41,7 @@ _HOST_SIGNATURES = {
     "spn_host_ogs_exchange_info": [c_void_p, c_int, c_void_p],
     "spn_host_ogs_array": [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_longlong)],
     "spn_host_ogs_halo_labels": [c_void_p, POINTER(c_void_p), POINTER(c_longlong)],
+    "spn_host_ogs_global_to_local": [c_void_p, c_void_p],
     "spn_host_ogs_gather_scatter": [c_void_p, c_void_p, c_int, c_int, c_int, c_int],
     "spn_host_ogs_gather_scatter_start": [c_void_p, c_void_p, c_int, c_int, c_int, c_int],
     "spn_host_ogs_gather_scatter_finish": [c_void_p, c_void_p, c_int, c_int, c_int, c_int],
@@ -200,6 +201,12 @@ class Ogs:
         if n.value == 0:
             return np.zeros(0, dtype=np.int64)
         return np.ctypeslib.as_array(ctypes.cast(p, POINTER(c_longlong)), shape=(n.value,)).copy()
+
+    def global_to_local(self):
+        """ogs_t::SetupGlobalToLocalMapping: row of every node in a gathered vector, -1 for masked nodes"""
+        out = np.empty(self.N, dtype=np.int32)
+        _check(host_lib().spn_host_ogs_global_to_local(self._h, out.ctypes.data), "global to local")
+        return out
 
     # ---- device operations (torch CUDA tensors as memory handles) ----
     def _sync_stream(self):

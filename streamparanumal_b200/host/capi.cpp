@@ -179,6 +179,11 @@ int spn_host_ogs_halo_labels(spn_host_ogs_t h, const long long** ptr, long long*
   return SPN_SUCCESS;
 }
 
+int spn_host_ogs_global_to_local(spn_host_ogs_t h, int* out) {
+  if (!h || !out) return SPN_ERR_INVALID_ARGUMENT;
+  return guarded([&] { h->ogs.SetupGlobalToLocalMapping(out); });
+}
+
 int spn_host_ogs_gather_scatter(spn_host_ogs_t h, void* v, int k, int type, int op, int trans) {
   if (!h) return SPN_ERR_INVALID_ARGUMENT;
   return guarded([&] {

@@ -129,6 +129,9 @@ class ogs_t {
              const bool verbose, platform_t& platform);
   // host-only plan (no CUDA calls): what the CPU tests of the partition/exchange logic use
   void SetupHost(const dlong N, hlong* ids, comm_t comm, const Kind kind, const bool unique, const bool verbose);
+  // GlobalToLocal[n] = position of node n's row in a gathered vector ([NlocalT local rows | halo rows]), -1 for a masked
+  // node; N entries (reference: ogs_t::SetupGlobalToLocalMapping, libs/ogs/ogsSetup.cpp:833-849).  A host index map.
+  void SetupGlobalToLocalMapping(dlong* GlobalToLocal) const;
   void Free();
 
   // ---- device operations: raw-pointer core (type-erased), used by the templates and the C API ----

@@ -450,6 +450,21 @@ void ogs_t::SetupPeerExchange() {
   p2p.enabled = true;
 }
 
+void ogs_t::SetupGlobalToLocalMapping(dlong* GlobalToLocal) const {
+  SPN_ABORT("ogs handle is not set up.", NgatherGlobal == 0 || !gatherLocal || !gatherHalo);  // ogsSetup.cpp:835-836
+#pragma omp parallel for
+  for (dlong n = 0; n < N; ++n) GlobalToLocal[n] = -1;
+  // the reference scatters the row numbers through both operators with NoTrans, i.e. over every copy (the T arrays)
+  const ogsOperator_t* ops[2] = {gatherLocal.get(), gatherHalo.get()};
+  const dlong base[2] = {0, NlocalT};
+  for (int o = 0; o < 2; ++o) {
+    const ogsOperator_t& op = *ops[o];
+#pragma omp parallel for
+    for (dlong r = 0; r < op.NrowsT; ++r)
+      for (dlong g = op.rowStartsT[r]; g < op.rowStartsT[r + 1]; ++g) GlobalToLocal[op.colIdsT[g]] = base[o] + r;
+  }
+}
+
 void ogs_t::AssertGatherDefined() const {
   SPN_ABORT("Gather / Scatter are not operations of a halo_t (Kind Halo): use Exchange / Combine", halo_only);
   SPN_ABORT("Gather operation not well-defined.", !gather_defined);  // libs/ogs/ogsSetup.cpp:827-830

@@ -230,5 +230,7 @@ def test_random_label_sets_against_the_live_reference(comm):
         for k, v in r.maps().items():
             if not k.startswith("block"):
                 assert np.array_equal(o.array("local_" + k)[: v.size], v), what + f": {k}"
+        if o.NgatherGlobal:   # ogs_t::SetupGlobalToLocalMapping (refused, as by the reference, when no label takes part)
+            assert np.array_equal(o.global_to_local(), r.global_to_local()), what + ": GlobalToLocal"
         r.close()
         o.close()

@@ -66,6 +66,7 @@ def _worker(rank, world, port, tmpdir, nx, ny, nz, p, element="Hex"):
             if k.startswith("block"):
                 continue
             assert np.array_equal(ogs.array("local_" + k)[: v.size], v), f"local {k} differs from the reference's"
+        assert np.array_equal(ogs.global_to_local(), ref.global_to_local()), "SetupGlobalToLocalMapping differs from the reference's"
         plan = ogs_sim.Plan(ogs)
         v = util.splitmix64(ids.size, 300 + rank)
         for tname, trans in (("Sym", host.SYM), ("NoTrans", host.NOTRANS), ("Trans", host.TRANS)):
